@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py — relational SpMM fwd+bwd throughput (edges/s) on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|small]
+
+A "step" is one pass of the hot path over one synthetic graph: S_r = A_r·X for every relation
+(iddgcn_spmm_fwd) followed by dX = Σ_r A_rᵀ·dS_r (iddgcn_spmm_bwd_x).  edges = Σ_r nnz_r (deduplicated).
+Workloads (BASELINE.json configs[2]/[3]):
+  c3    N=1M nodes, 2 relations x 10M raw edges, D=128, one B200.  With --gpus P the graph is P x c3
+        (P·1M nodes, P·20M edges), destination rows partitioned into P blocks of 1M rows (weak scaling):
+        per step every rank all-gathers the feature blocks (NCCL), runs its row block fwd + bwd, and
+        reduce-scatters the partial dX.
+  c4    N=20M nodes, 2 x 100M raw edges, D=128, same partitioning, total work fixed (strong scaling).
+  small N=100k, 2 x 1M edges (smoke-sized).
+Timing: CUDA events on the launching stream, W warm-up steps then K timed steps bracketed by barrier +
+synchronize; max over ranks.  Inputs (X 0.5 GB, dS 1 GB, S 1 GB at c3) are far larger than the 126 MB
+L2, so no explicit flush is needed between iterations (stated in config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak"),
+    "c4": dict(N=20_000_000, R=2, per_rel=100_000_000, D=128, scaling="strong"),
+    "small": dict(N=100_000, R=2, per_rel=1_000_000, D=128, scaling="weak"),
+}
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def algorithmic_bytes(nnz, n_rows, n_cols, R, D):
+    """SURVEY §8(d) gather model: every edge fetches its 4D-byte source row and a 4-byte index."""
+    fwd = nnz * (4 * D + 4) + R * n_rows * 4 * D + R * (n_rows + 1) * 4
+    bwd = nnz * (4 * D + 4) + n_cols * 4 * D + R * (n_cols + 1) * 4
+    return fwd, bwd
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed):
+    """Uniform random directed edges (SURVEY §8d recipe, generated on device): per relation
+    per_rel_total (head, tail) pairs; a rank keeps only heads inside its row block."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = []
+    chunk = 25_000_000
+    for r in range(R):
+        gen = torch.Generator(device=dev).manual_seed(seed * 1000 + r)
+        left = per_rel_total
+        while left > 0:
+            n = min(chunk, left)
+            h = torch.randint(0, N_total, (n,), device=dev, generator=gen)
+            t = torch.randint(0, N_total, (n,), device=dev, generator=gen)
+            if row_lo != 0 or row_hi != N_total:
+                keep = (h >= row_lo) & (h < row_hi)
+                h, t = h[keep], t[keep]
+            out.append(torch.stack([h, torch.full_like(h, r), t], 1))
+            left -= n
+    return torch.cat(out, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle; the one place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_run(struct, N, n_rows, R, D, X, dS, passes, threads=0):
+    from oracle import cref
+    S = np.empty((R * n_rows, D), np.float32)
+    dX = np.empty((N, D), np.float32)
+    times = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        cref.spmm_csr(struct["csr_rowptr"], struct["csr_col"], None, X, out=S, threads=threads)
+        cref.spmm_csc_bwd(struct["csc_rowptr"], struct["csc_row"], struct["csc_perm"], None, R, N, n_rows, dS, out=dX,
+                          threads=threads)
+        times.append(time.perf_counter() - t0)
+    return times, (cref.max_threads() if threads == 0 else threads)
+
+
+def cpu_sample_inputs(wl, seed=0):
+    """Host-side (NumPy) generation of the CPU arm's inputs with the SURVEY §8d recipe.  c3/small run
+    the FULL workload; c4 (200M edges) is bounded to the same generator at 1/8 scale."""
+    rng = np.random.default_rng(seed)
+    frac = 8 if wl["per_rel"] > 20_000_000 else 1
+    N, R, D = wl["N"] // frac, wl["R"], wl["D"]
+    n_rows = N
+    per_rel = wl["per_rel"] // frac
+    rows_all, cols_all, perm_all, crow_all = [], [], [], []
+    rowptr = np.zeros(R * n_rows + 1, np.int64)
+    cptr = np.zeros(R * N + 1, np.int64)
+    off = 0
+    for r in range(R):
+        h = rng.integers(0, n_rows, per_rel)
+        t = rng.integers(0, N, per_rel)
+        key = np.unique(h * N + t)                      # dedup + (head, tail) order = CSR order
+        rows, cols = key // N, key % N
+        rowptr[r * n_rows + 1:(r + 1) * n_rows + 1] = off + np.cumsum(np.bincount(rows, minlength=n_rows))
+        order = np.argsort(cols * n_rows + rows, kind="stable")      # (tail, head) order = CSC order
+        cptr[r * N + 1:(r + 1) * N + 1] = off + np.cumsum(np.bincount(cols, minlength=N))
+        rows_all.append(rows); cols_all.append(cols); perm_all.append(order + off); crow_all.append(rows[order])
+        off += len(key)
+    nnz = off
+    struct = {"csr_rowptr": rowptr.astype(np.int32), "csr_col": np.concatenate(cols_all).astype(np.int32),
+              "csc_rowptr": cptr.astype(np.int32), "csc_row": np.concatenate(crow_all).astype(np.int32),
+              "csc_perm": np.concatenate(perm_all).astype(np.int32)}
+    X = rng.random((N, D), dtype=np.float32)
+    dS = rng.standard_normal((R * n_rows, D), dtype=np.float32)
+    scale = "full workload" if frac == 1 else f"same generator at 1/{frac} scale"
+    sample = f"{wl['name']} ({scale}): {N} nodes, {nnz} edges, R={R}, D={D}, one fwd+bwd pass per step"
+    return struct, N, n_rows, nnz, X, dS, sample
+
+
+def run_reference(args, wl):
+    """--impl reference: the CPU restatement (oracle/spmm_ref.c, OpenMP over all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    struct, N, n_rows, nnz, X, dS, sample = cpu_sample_inputs(wl)
+    R, D = wl["R"], wl["D"]
+    cpu_baseline_run(struct, N, n_rows, R, D, X, dS, max(args.warmup, 1))
+    times, cores = cpu_baseline_run(struct, N, n_rows, R, D, X, dS, args.steps)
+    total = sum(times)
+    value = nnz * args.steps / total
+    line = {
+        "impl": "reference", "metric": "relational_spmm_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": wl["label"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from iddgcn_b200 import _lib, ops
+    from iddgcn_b200.graph import Graph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R, D = wl["R"], wl["D"]
+    if wl["scaling"] == "weak":
+        N_total, per_rel_total = wl["N"] * world, wl["per_rel"] * world
+    else:
+        N_total, per_rel_total = wl["N"], wl["per_rel"]
+    block = (N_total + world - 1) // world
+    row_lo, row_hi = rank * block, min((rank + 1) * block, N_total)
+    n_rows = row_hi - row_lo
+
+    tri = make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed=7)
+    t0 = time.perf_counter()
+    g = Graph(tri, N_total, R, row_block=(row_lo, row_hi))
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    del tri
+    torch.cuda.empty_cache()
+    nnz_local = g.nnz
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X_local = torch.rand((n_rows, D), device=dev, generator=gen)      # this rank's block of the features
+    dS = torch.randn((R, n_rows, D), device=dev, generator=gen)
+    S = torch.empty((R, n_rows, D), device=dev)
+    if world > 1:
+        from iddgcn_b200.dist import PartitionedSpMM
+        engine = PartitionedSpMM(g, D, world, rank, block)
+        step = lambda: engine.step(X_local, dS, S)
+        nnz_t = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(nnz_t)
+        nnz_global = int(nnz_t.item())
+    else:
+        dX = torch.empty((N_total, D), device=dev)
+
+        def step():
+            ops.spmm_fwd(g, X_local, out=S)
+            ops.spmm_bwd_x(g, dS, out=dX)
+        nnz_global = nnz_local
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = nnz_global / (ms_per_step * 1e-3)
+
+    # per-kernel timing (events on the launching stream) for the roofline of the dominant kernel
+    kt = {"fwd": [], "bwd": []}
+    if world == 1:
+        for _ in range(max(args.steps, 5)):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record(); ops.spmm_fwd(g, X_local, out=S); b.record(); ops.spmm_bwd_x(g, dS, out=dX); c.record()
+            torch.cuda.synchronize()
+            kt["fwd"].append(a.elapsed_time(b)); kt["bwd"].append(b.elapsed_time(c))
+    else:
+        kt = engine.kernel_times(X_local, dS, S, iters=max(args.steps, 5))
+    fwd_ms, bwd_ms = float(np.mean(kt["fwd"])), float(np.mean(kt["bwd"]))
+    bf, bb = algorithmic_bytes(nnz_local, n_rows, N_total, R, D)
+    peak, peak_src = hbm_peak()
+    dom = "fwd" if fwd_ms >= bwd_ms else "bwd"
+    dom_bytes, dom_ms = (bf, fwd_ms) if dom == "fwd" else (bb, bwd_ms)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj.get(wl["name"], {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": f"gather_rows_kernel ({'spmm_fwd' if dom == 'fwd' else 'spmm_bwd_x'})",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
+                "fwd": {"ms": fwd_ms, "bytes": bf, "GBps": bf / fwd_ms / 1e6, "frac": bf / fwd_ms / 1e6 / peak},
+                "bwd": {"ms": bwd_ms, "bytes": bb, "GBps": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
+                "step_frac": (bf + bb) / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    # end-to-end through the C ABI with HOST buffers (pinned): H2D + fwd + bwd + D2H every step
+    e2e = None
+    if world == 1:
+        Xh = X_local.cpu().pin_memory(); dSh = dS.cpu().pin_memory()
+        Sh = torch.empty((R, n_rows, D)).pin_memory(); dXh = torch.empty((N_total, D)).pin_memory()
+        del S, dX, X_local, dS
+        torch.cuda.empty_cache()
+        k2 = max(3, min(args.steps, 5))
+        for _ in range(2):
+            ops.spmm_fwd_bwd_host(g, Xh, dSh, Sh, dXh)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            ops.spmm_fwd_bwd_host(g, Xh, dSh, Sh, dXh)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / k2
+        e2e = {"value": nnz_global / dt, "unit": "edges/s", "h2d_bytes_per_step": Xh.numel() * 4 + dSh.numel() * 4,
+               "d2h_bytes_per_step": Sh.numel() * 4 + dXh.numel() * 4, "ms_per_step": dt * 1e3, "steps": k2,
+               "launches_per_step": (_lib.launch_count() - l0) / k2,
+               "api": "iddgcn_spmm_fwd_bwd_host (pinned host buffers in/out)"}
+        del Xh, dSh, Sh, dXh
+    else:
+        e2e = engine.e2e(args, nnz_global)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if wl["per_rel"] <= 20_000_000:
+            # the very graph and inputs the GPU just ran, exported through the C ABI
+            struct = g.export()
+            cN, cn_rows, cnnz = N_total, n_rows, nnz_local
+            gen = torch.Generator().manual_seed(5)
+            cX = torch.rand((cN, D), generator=gen).numpy()
+            cdS = torch.randn((R * cn_rows, D), generator=gen).numpy()
+            sample = f"{wl['name']} (full workload, the graph the GPU ran): {cN} nodes, {cnnz} edges, 2 timed passes"
+        else:
+            struct, cN, cn_rows, cnnz, cX, cdS, sample = cpu_sample_inputs(wl)
+        cpu_baseline_run(struct, cN, cn_rows, R, D, cX, cdS, 1)
+        times, cores = cpu_baseline_run(struct, cN, cn_rows, R, D, cX, cdS, 2)
+        cpu = {"value": cnnz * len(times) / sum(times), "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": sample, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        line = {
+            "metric": "relational_spmm_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "nodes": N_total, "edges": nnz_global, "relations": R,
+                       "feature_dim": D, "rows_per_gpu": n_rows, "partition": f"dest-row blocks x{world}",
+                       "l2": "inputs larger than L2 (no flush needed)", "graph_build_s": build_s},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = dict(WORKLOADS[args.workload])
+    wl["name"] = args.workload
+    wl["label"] = {
+        "c3": "synthetic 1M-node / 20M-edge 2-relation directed graph, D=128 (BASELINE configs[2]); "
+              "xP row-partitioned at --gpus P (configs[3] recipe, weak)",
+        "c4": "synthetic 20M-node / 200M-edge 2-relation graph, D=128, destination-row partitioned (configs[3])",
+        "small": "synthetic 100k-node / 2M-edge 2-relation graph, D=128 (smoke size)",
+    }[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch ourselves under torchrun when called as plain `python bench.py --gpus N`
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,444 @@
+// graph_build.cu — triples -> relation-segmented CSR + CSC, entirely on device.
+//
+// Replaces utils1.get_adj_mats / distinct (prediction/utils1.py:415-451): per relation keep
+// (head, tail) of rows with rel == i, np.unique(axis=0) (lexicographic sort + dedup).  Here all
+// relations are handled at once by sorting packed keys (rel | head | tail); the result is
+// bit-exact w.r.t. the reference (integer work, deterministic sort).
+#include "graph.cuh"
+#include "primitives.cuh"
+
+namespace iddgcn {
+
+struct KeyLayout {
+  int bt;  // bits of the low field
+  int bh;  // bits of the middle field
+  int br;  // bits of rel
+  __host__ __device__ int total() const { return bt + bh + br; }
+};
+
+// key = rel << (bh+bt) | (head-row_lo) << bt | tail ; invalid rows get bit `total` set.
+__global__ void pack_keys_kernel(const int64_t* __restrict__ triples, size_t M, int64_t N, int R, int64_t row_lo,
+                                 int64_t row_hi, KeyLayout L, uint64_t* __restrict__ keys, int* __restrict__ err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int64_t h = triples[3 * i + 0];
+  const int64_t r = triples[3 * i + 1];
+  const int64_t t = triples[3 * i + 2];
+  const uint64_t invalid = 1ull << L.total();
+  uint64_t key = invalid;
+  if (r >= 0 && r < (int64_t)R) {
+    if (h < 0 || h >= N || t < 0 || t >= N) {
+      *err = 1;  // benign race: every writer stores 1
+    } else if (h >= row_lo && h < row_hi) {
+      key = ((uint64_t)r << (L.bh + L.bt)) | ((uint64_t)(h - row_lo) << L.bt) | (uint64_t)t;
+    }
+  }
+  keys[i] = key;
+}
+
+__global__ void unique_flag_kernel(const uint64_t* __restrict__ keys, size_t M, uint64_t invalid,
+                                   uint32_t* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > M) return;
+  uint32_t f = 0;
+  if (i < M) {
+    const uint64_t k = keys[i];
+    f = (k < invalid) && (i == 0 || keys[i - 1] != k);
+  }
+  flags[i] = f;  // flags[M] = 0 so that the scan yields the total at [M]
+}
+
+__global__ void unique_compact_kernel(const uint64_t* __restrict__ keys, size_t M, uint64_t invalid,
+                                      const uint32_t* __restrict__ pos, uint64_t* __restrict__ ukeys) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const uint64_t k = keys[i];
+  if ((k < invalid) && (i == 0 || keys[i - 1] != k)) ukeys[pos[i]] = k;
+}
+
+// CSR edge arrays from the unique sorted keys, and the (rel | tail | head) keys for the CSC sort.
+__global__ void decode_csr_kernel(const uint64_t* __restrict__ ukeys, size_t nnz, KeyLayout L,
+                                  int32_t* __restrict__ col, int32_t* __restrict__ row,
+                                  uint64_t* __restrict__ keys2, uint32_t* __restrict__ eid) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  const uint64_t k = ukeys[e];
+  const uint64_t t = k & ((1ull << L.bt) - 1ull);
+  const uint64_t h = (k >> L.bt) & ((1ull << L.bh) - 1ull);
+  const uint64_t r = k >> (L.bt + L.bh);
+  col[e] = (int32_t)t;
+  row[e] = (int32_t)h;
+  keys2[e] = (r << (L.bh + L.bt)) | (t << L.bh) | h;
+  eid[e] = (uint32_t)e;
+}
+
+__global__ void decode_csc_kernel(const uint64_t* __restrict__ keys2, const uint32_t* __restrict__ eid, size_t nnz,
+                                  KeyLayout L, int32_t* __restrict__ csc_row, int32_t* __restrict__ csc_perm) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  csc_row[e] = (int32_t)(keys2[e] & ((1ull << L.bh) - 1ull));
+  csc_perm[e] = (int32_t)eid[e];
+}
+
+// ptr[s] = lower_bound(keys, (s / seg_len) << hi_shift | (s % seg_len) << lo_shift); ptr[num_segs] = nnz
+__global__ void segment_ptr_kernel(const uint64_t* __restrict__ keys, size_t nnz, size_t num_segs, uint64_t seg_len,
+                                   int hi_shift, int lo_shift, int32_t* __restrict__ ptr) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > num_segs) return;
+  if (s == num_segs) {
+    ptr[s] = (int32_t)nnz;
+    return;
+  }
+  const uint64_t target = ((uint64_t)(s / seg_len) << hi_shift) | ((uint64_t)(s % seg_len) << lo_shift);
+  size_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  ptr[s] = (int32_t)lo;
+}
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device, int64_t N, int R, int64_t row_lo,
+                            int64_t row_hi, cudaStream_t st, iddgcn_graph* g) {
+  const int64_t n_rows = row_hi - row_lo;
+  KeyLayout L;
+  L.bt = ceil_log2_u64((uint64_t)(N - 1));
+  L.bh = ceil_log2_u64((uint64_t)(n_rows - 1));
+  L.br = ceil_log2_u64((uint64_t)(R - 1));
+  if (L.bt < 1) L.bt = 1;
+  if (L.bh < 1) L.bh = 1;
+  if (L.br < 1) L.br = 1;
+  IDD_CHECK(L.total() + 1 <= 63, IDDGCN_ELIMIT, "key does not fit 63 bits (N=%lld, R=%d)", (long long)N, R);
+  const size_t csr_segs = (size_t)R * (size_t)n_rows;
+  const size_t csc_segs = (size_t)R * (size_t)N;
+  IDD_CHECK(M < (int64_t)0x7fffff00 && csc_segs < (size_t)0x7fffff00 && csr_segs < (size_t)0x7fffff00, IDDGCN_ELIMIT,
+            "graph exceeds int32 index range (M=%lld, R*N=%zu)", (long long)M, csc_segs);
+
+  g->N = N; g->n_rows = n_rows; g->row_lo = row_lo; g->R = R;
+  g->nnz_rel.assign(R, 0);
+  IDD_CUDA(cudaGetDevice(&g->device));
+  IDD_CUDA(cudaMalloc((void**)&g->csr_rowptr, (csr_segs + 1) * sizeof(int32_t)));
+  IDD_CUDA(cudaMalloc((void**)&g->csc_rowptr, (csc_segs + 1) * sizeof(int32_t)));
+  IDD_CUDA(cudaMalloc((void**)&g->rel_sums_scratch, (size_t)(R > 0 ? R : 1) * sizeof(float)));
+
+  const size_t Mz = (size_t)M;
+  DevBuf<int64_t> trip_tmp;
+  const int64_t* triples = triples_in;
+  if (!on_device && Mz) {
+    IDD_CUDA(trip_tmp.ensure(Mz * 3));
+    IDD_CUDA(cudaMemcpyAsync(trip_tmp.p, triples_in, Mz * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    triples = trip_tmp.p;
+  }
+
+  size_t nnz = 0;
+  DevBuf<uint64_t> kA, kB;
+  DevBuf<uint32_t> vA, vB, hist, scratch, flags;
+  DevBuf<int> err;
+  uint64_t* ukeys = nullptr;
+  if (Mz) {
+    const RadixSortPlan plan = radix_sort_plan(Mz);
+    IDD_CUDA(kA.ensure(Mz));
+    IDD_CUDA(kB.ensure(Mz));
+    IDD_CUDA(hist.ensure(plan.hist_elems));
+    const size_t scr = plan.scratch_elems > scan_scratch_elems(Mz + 1) ? plan.scratch_elems : scan_scratch_elems(Mz + 1);
+    IDD_CUDA(scratch.ensure(scr));
+    IDD_CUDA(flags.ensure(Mz + 1));
+    IDD_CUDA(err.ensure(1));
+    IDD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+
+    pack_keys_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(triples, Mz, N, R, row_lo, row_hi, L, kA.p, err.p);
+    IDD_LAUNCH_CHECK();
+    uint64_t* sorted = nullptr;
+    IDD_TRY(radix_sort_u64(kA.p, kB.p, nullptr, nullptr, Mz, L.total() + 1, plan, hist.p, scratch.p, st, &sorted,
+                           nullptr));
+    uint64_t* other = (sorted == kA.p) ? kB.p : kA.p;
+    const uint64_t invalid = 1ull << L.total();
+    unique_flag_kernel<<<blocks_for(Mz + 1, 256), 256, 0, st>>>(sorted, Mz, invalid, flags.p);
+    IDD_LAUNCH_CHECK();
+    IDD_TRY(exclusive_scan_u32(flags.p, flags.p, Mz + 1, scratch.p, st));
+    unique_compact_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(sorted, Mz, invalid, flags.p, other);
+    IDD_LAUNCH_CHECK();
+    uint32_t nnz32 = 0;
+    int herr = 0;
+    IDD_CUDA(cudaMemcpyAsync(&nnz32, flags.p + Mz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    IDD_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IDD_CUDA(cudaStreamSynchronize(st));
+    IDD_CHECK(herr == 0, IDDGCN_ERANGE, "triples contain an entity index outside [0, %lld)", (long long)N);
+    nnz = nnz32;
+    ukeys = other;  // `sorted` is now free to be reused
+    // CSR
+    const size_t alloc_e = nnz ? nnz : 1;
+    IDD_CUDA(cudaMalloc((void**)&g->csr_col, alloc_e * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csr_row, alloc_e * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csc_row, alloc_e * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csc_perm, alloc_e * sizeof(int32_t)));
+    segment_ptr_kernel<<<blocks_for(csr_segs + 1, 256), 256, 0, st>>>(ukeys, nnz, csr_segs, (uint64_t)n_rows,
+                                                                      L.bh + L.bt, L.bt, g->csr_rowptr);
+    IDD_LAUNCH_CHECK();
+    if (nnz) {
+      IDD_CUDA(vA.ensure(nnz));
+      IDD_CUDA(vB.ensure(nnz));
+      uint64_t* keys2 = sorted;
+      decode_csr_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(ukeys, nnz, L, g->csr_col, g->csr_row, keys2, vA.p);
+      IDD_LAUNCH_CHECK();
+      const RadixSortPlan plan2 = radix_sort_plan(nnz);  // nnz <= M: hist/scratch are large enough
+      uint64_t* s2 = nullptr;
+      uint32_t* sv = nullptr;
+      IDD_TRY(radix_sort_u64(keys2, ukeys, vA.p, vB.p, nnz, L.total(), plan2, hist.p, scratch.p, st, &s2, &sv));
+      decode_csc_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(s2, sv, nnz, L, g->csc_row, g->csc_perm);
+      IDD_LAUNCH_CHECK();
+      segment_ptr_kernel<<<blocks_for(csc_segs + 1, 256), 256, 0, st>>>(s2, nnz, csc_segs, (uint64_t)N, L.bh + L.bt,
+                                                                        L.bh, g->csc_rowptr);
+      IDD_LAUNCH_CHECK();
+    } else {
+      IDD_CUDA(cudaMemsetAsync(g->csc_rowptr, 0, (csc_segs + 1) * sizeof(int32_t), st));
+    }
+  } else {
+    IDD_CUDA(cudaMalloc((void**)&g->csr_col, sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csr_row, sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csc_row, sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->csc_perm, sizeof(int32_t)));
+    IDD_CUDA(cudaMemsetAsync(g->csr_rowptr, 0, (csr_segs + 1) * sizeof(int32_t), st));
+    IDD_CUDA(cudaMemsetAsync(g->csc_rowptr, 0, (csc_segs + 1) * sizeof(int32_t), st));
+  }
+  g->nnz = (int64_t)nnz;
+  // per-relation counts: R+1 strided reads of the CSR row pointer
+  std::vector<int32_t> bounds(R + 1, 0);
+  for (int r = 0; r <= R; ++r)
+    IDD_CUDA(cudaMemcpyAsync(&bounds[r], g->csr_rowptr + (size_t)r * n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                             st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < R; ++r) g->nnz_rel[r] = (int64_t)bounds[r + 1] - bounds[r];
+  return IDDGCN_OK;
+}
+
+static void graph_free(iddgcn_graph* g) {
+  if (!g) return;
+  cudaFree(g->csr_rowptr); cudaFree(g->csr_col); cudaFree(g->csr_row);
+  cudaFree(g->csc_rowptr); cudaFree(g->csc_row); cudaFree(g->csc_perm);
+  cudaFree(g->rel_sums_scratch);
+  delete g;
+}
+
+// ---------------------------------------------------------------------------
+// plan: int32 copies of (head, rel, tail) + sort-by-head / by-tail / by-rel permutations
+// ---------------------------------------------------------------------------
+__global__ void plan_pack_kernel(const int64_t* __restrict__ head, const int64_t* __restrict__ rel,
+                                 const int64_t* __restrict__ tail, size_t T, int64_t N, int R,
+                                 int32_t* __restrict__ h32, int32_t* __restrict__ r32, int32_t* __restrict__ t32,
+                                 int* __restrict__ err) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int64_t h = head[i], r = rel[i], t = tail[i];
+  if (h < 0 || h >= N || t < 0 || t >= N || r < 0 || r >= R) *err = 1;
+  h32[i] = (int32_t)h; r32[i] = (int32_t)r; t32[i] = (int32_t)t;
+}
+
+__global__ void plan_keys_kernel(const int32_t* __restrict__ field, size_t T, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ ids) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  keys[i] = (uint64_t)(uint32_t)field[i];
+  ids[i] = (uint32_t)i;
+}
+
+__global__ void copy_u32_to_i32_kernel(const uint32_t* __restrict__ in, size_t n, int32_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int32_t)in[i];
+}
+
+static int plan_sort_by(const int32_t* field, size_t T, size_t num_bins, int bits, uint64_t* kA, uint64_t* kB,
+                        uint32_t* vA, uint32_t* vB, const RadixSortPlan& plan, uint32_t* hist, uint32_t* scratch,
+                        cudaStream_t st, int32_t* perm_out, int32_t* ptr_out) {
+  plan_keys_kernel<<<blocks_for(T, 256), 256, 0, st>>>(field, T, kA, vA);
+  IDD_LAUNCH_CHECK();
+  uint64_t* ks = nullptr;
+  uint32_t* vs = nullptr;
+  IDD_TRY(radix_sort_u64(kA, kB, vA, vB, T, bits, plan, hist, scratch, st, &ks, &vs));
+  copy_u32_to_i32_kernel<<<blocks_for(T, 256), 256, 0, st>>>(vs, T, perm_out);
+  IDD_LAUNCH_CHECK();
+  // key == bin index: seg_len = num_bins+1 keeps s / seg_len == 0 for every s <= num_bins
+  segment_ptr_kernel<<<blocks_for(num_bins + 1, 256), 256, 0, st>>>(ks, T, num_bins, (uint64_t)num_bins + 1, 40, 0,
+                                                                    ptr_out);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64_t* tail, int64_t T, int on_device,
+                            int64_t N, int R, cudaStream_t st, iddgcn_plan* p) {
+  IDD_CUDA(cudaGetDevice(&p->device));
+  p->T = T; p->N = N; p->R = R;
+  const size_t Tz = (size_t)T;
+  const size_t Ta = Tz ? Tz : 1;
+  IDD_CUDA(cudaMalloc((void**)&p->head, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->rel, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->tail, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_head_perm, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_tail_perm, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_rel_perm, Ta * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_head_ptr, ((size_t)N + 1) * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_tail_ptr, ((size_t)N + 1) * 4));
+  IDD_CUDA(cudaMalloc((void**)&p->by_rel_ptr, ((size_t)R + 1) * 4));
+  if (!Tz) {
+    IDD_CUDA(cudaMemsetAsync(p->by_head_ptr, 0, ((size_t)N + 1) * 4, st));
+    IDD_CUDA(cudaMemsetAsync(p->by_tail_ptr, 0, ((size_t)N + 1) * 4, st));
+    IDD_CUDA(cudaMemsetAsync(p->by_rel_ptr, 0, ((size_t)R + 1) * 4, st));
+    IDD_CUDA(cudaStreamSynchronize(st));
+    return IDDGCN_OK;
+  }
+  DevBuf<int64_t> tmp;
+  const int64_t *dh = head, *dr = rel, *dt = tail;
+  if (!on_device) {
+    IDD_CUDA(tmp.ensure(Tz * 3));
+    IDD_CUDA(cudaMemcpyAsync(tmp.p, head, Tz * 8, cudaMemcpyHostToDevice, st));
+    IDD_CUDA(cudaMemcpyAsync(tmp.p + Tz, rel, Tz * 8, cudaMemcpyHostToDevice, st));
+    IDD_CUDA(cudaMemcpyAsync(tmp.p + 2 * Tz, tail, Tz * 8, cudaMemcpyHostToDevice, st));
+    dh = tmp.p; dr = tmp.p + Tz; dt = tmp.p + 2 * Tz;
+  }
+  DevBuf<int> err;
+  IDD_CUDA(err.ensure(1));
+  IDD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+  plan_pack_kernel<<<blocks_for(Tz, 256), 256, 0, st>>>(dh, dr, dt, Tz, N, R, p->head, p->rel, p->tail, err.p);
+  IDD_LAUNCH_CHECK();
+  int herr = 0;
+  IDD_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  IDD_CHECK(herr == 0, IDDGCN_ERANGE, "triple index outside [0,%lld) or relation outside [0,%d)", (long long)N, R);
+
+  const RadixSortPlan plan = radix_sort_plan(Tz);
+  DevBuf<uint64_t> kA, kB;
+  DevBuf<uint32_t> vA, vB, hist, scratch;
+  IDD_CUDA(kA.ensure(Tz)); IDD_CUDA(kB.ensure(Tz)); IDD_CUDA(vA.ensure(Tz)); IDD_CUDA(vB.ensure(Tz));
+  IDD_CUDA(hist.ensure(plan.hist_elems));
+  IDD_CUDA(scratch.ensure(plan.scratch_elems));
+  const int bn = ceil_log2_u64((uint64_t)(N > 1 ? N - 1 : 1));
+  const int brr = ceil_log2_u64((uint64_t)(R > 1 ? R - 1 : 1));
+  IDD_TRY(plan_sort_by(p->head, Tz, (size_t)N, bn, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
+                       p->by_head_perm, p->by_head_ptr));
+  IDD_TRY(plan_sort_by(p->tail, Tz, (size_t)N, bn, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
+                       p->by_tail_perm, p->by_tail_ptr));
+  IDD_TRY(plan_sort_by(p->rel, Tz, (size_t)R, brr, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
+                       p->by_rel_perm, p->by_rel_ptr));
+  IDD_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
+  return IDDGCN_OK;
+}
+
+static void plan_free(iddgcn_plan* p) {
+  if (!p) return;
+  cudaFree(p->head); cudaFree(p->rel); cudaFree(p->tail);
+  cudaFree(p->by_head_perm); cudaFree(p->by_head_ptr);
+  cudaFree(p->by_tail_perm); cudaFree(p->by_tail_ptr);
+  cudaFree(p->by_rel_perm); cudaFree(p->by_rel_ptr);
+  delete p;
+}
+
+}  // namespace iddgcn
+
+using namespace iddgcn;
+
+extern "C" {
+
+int iddgcn_graph_build(const int64_t* triples, int64_t M, int triples_on_device, int64_t num_entities,
+                       int num_relations, int64_t row_lo, int64_t row_hi, void* stream, iddgcn_graph_t** out) {
+  IDD_CHECK(out != nullptr, IDDGCN_EINVAL, "out is NULL");
+  *out = nullptr;
+  IDD_CHECK(M >= 0 && (M == 0 || triples != nullptr), IDDGCN_EINVAL, "triples is NULL with M=%lld", (long long)M);
+  IDD_CHECK(num_entities > 0 && num_relations > 0, IDDGCN_EINVAL, "num_entities and num_relations must be positive");
+  IDD_CHECK(row_lo >= 0 && row_lo < row_hi && row_hi <= num_entities, IDDGCN_EINVAL,
+            "row block [%lld,%lld) is not inside [0,%lld)", (long long)row_lo, (long long)row_hi,
+            (long long)num_entities);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libiddgcn_b200 has no CPU fallback");
+    return IDDGCN_ECUDA;
+  }
+  iddgcn_graph* g = new iddgcn_graph();
+  int rc = graph_build_impl(triples, M, triples_on_device, num_entities, num_relations, row_lo, row_hi,
+                            (cudaStream_t)stream, g);
+  if (rc != IDDGCN_OK) {
+    graph_free(g);
+    return rc;
+  }
+  *out = g;
+  return IDDGCN_OK;
+}
+
+int iddgcn_graph_destroy(iddgcn_graph_t* g) {
+  graph_free(g);
+  return IDDGCN_OK;
+}
+
+int iddgcn_graph_info(const iddgcn_graph_t* g, int64_t* num_entities, int* num_relations, int64_t* n_rows,
+                      int64_t* row_lo, int64_t* nnz, int64_t* nnz_per_rel) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  if (num_entities) *num_entities = g->N;
+  if (num_relations) *num_relations = g->R;
+  if (n_rows) *n_rows = g->n_rows;
+  if (row_lo) *row_lo = g->row_lo;
+  if (nnz) *nnz = g->nnz;
+  if (nnz_per_rel)
+    for (int r = 0; r < g->R; ++r) nnz_per_rel[r] = g->nnz_rel[r];
+  return IDDGCN_OK;
+}
+
+int iddgcn_graph_export_host(const iddgcn_graph_t* g, int32_t* csr_rowptr, int32_t* csr_col, int32_t* csr_row,
+                             int32_t* csc_rowptr, int32_t* csc_row, int32_t* csc_perm) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  const size_t e = (size_t)g->nnz * sizeof(int32_t);
+  if (csr_rowptr)
+    IDD_CUDA(cudaMemcpy(csr_rowptr, g->csr_rowptr, ((size_t)g->R * g->n_rows + 1) * 4, cudaMemcpyDeviceToHost));
+  if (csc_rowptr)
+    IDD_CUDA(cudaMemcpy(csc_rowptr, g->csc_rowptr, ((size_t)g->R * g->N + 1) * 4, cudaMemcpyDeviceToHost));
+  if (e) {
+    if (csr_col) IDD_CUDA(cudaMemcpy(csr_col, g->csr_col, e, cudaMemcpyDeviceToHost));
+    if (csr_row) IDD_CUDA(cudaMemcpy(csr_row, g->csr_row, e, cudaMemcpyDeviceToHost));
+    if (csc_row) IDD_CUDA(cudaMemcpy(csc_row, g->csc_row, e, cudaMemcpyDeviceToHost));
+    if (csc_perm) IDD_CUDA(cudaMemcpy(csc_perm, g->csc_perm, e, cudaMemcpyDeviceToHost));
+  }
+  return IDDGCN_OK;
+}
+
+int iddgcn_graph_device_ptrs(const iddgcn_graph_t* g, const int32_t** csr_rowptr, const int32_t** csr_col,
+                             const int32_t** csr_row, const int32_t** csc_rowptr, const int32_t** csc_row,
+                             const int32_t** csc_perm) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  if (csr_rowptr) *csr_rowptr = g->csr_rowptr;
+  if (csr_col) *csr_col = g->csr_col;
+  if (csr_row) *csr_row = g->csr_row;
+  if (csc_rowptr) *csc_rowptr = g->csc_rowptr;
+  if (csc_row) *csc_row = g->csc_row;
+  if (csc_perm) *csc_perm = g->csc_perm;
+  return IDDGCN_OK;
+}
+
+int iddgcn_plan_create(const int64_t* head, const int64_t* rel, const int64_t* tail, int64_t T, int on_device,
+                       int64_t num_entities, int num_relations, void* stream, iddgcn_plan_t** out) {
+  IDD_CHECK(out != nullptr, IDDGCN_EINVAL, "out is NULL");
+  *out = nullptr;
+  IDD_CHECK(T >= 0 && (T == 0 || (head && rel && tail)), IDDGCN_EINVAL, "NULL triple arrays with T=%lld",
+            (long long)T);
+  IDD_CHECK(T < (int64_t)0x7fffff00, IDDGCN_ELIMIT, "T exceeds int32 range");
+  IDD_CHECK(num_entities > 0 && num_relations > 0, IDDGCN_EINVAL, "num_entities and num_relations must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libiddgcn_b200 has no CPU fallback");
+    return IDDGCN_ECUDA;
+  }
+  iddgcn_plan* p = new iddgcn_plan();
+  int rc = plan_create_impl(head, rel, tail, T, on_device, num_entities, num_relations, (cudaStream_t)stream, p);
+  if (rc != IDDGCN_OK) {
+    plan_free(p);
+    return rc;
+  }
+  *out = p;
+  return IDDGCN_OK;
+}
+
+int iddgcn_plan_destroy(iddgcn_plan_t* p) {
+  plan_free(p);
+  return IDDGCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,468 @@
+// spmm.cu — relational SpMM forward, transposed backward, and SDDMM (edge-value gradient).
+//
+// Replaces tf.sparse.sparse_dense_matmul(adj_i, embeddings) (prediction/IDDGCN.py:70) for all
+// relations in one launch, plus its TF gradient w.r.t. the dense operand (adjoint SpMM) and
+// w.r.t. the sparse values (explanation/explaiNE.py:17, GnnExplainer.py:51).
+//
+// HBM-bound gather kernels: one sub-warp of LPR lanes owns one output row; every lane keeps
+// float4 accumulators for its 16-byte slice(s) of the feature row; edge indices of a row are
+// loaded coalesced (one per lane) and broadcast by shuffle; U independent 128-bit row gathers
+// are issued before any is consumed.  The forward walks CSR rows (r, head); the backward
+// walks CSC rows (r, tail) with all relations fused into a single dX write, so neither needs
+// atomics and the summation order is fixed (ascending neighbour index, as TF-CPU does).
+// Edge weights (explicit values or sigmoid(mask)) are applied in registers.
+#include "graph.cuh"
+
+namespace iddgcn {
+
+constexpr int SPMM_THREADS = 256;
+
+template <int MODE>
+__device__ __forceinline__ float edge_weight(const float* __restrict__ vals, int e) {
+  if (MODE == IDDGCN_VALS_ONES) return 1.0f;
+  const float v = __ldg(vals + e);
+  if (MODE == IDDGCN_VALS_SIGMOID) return sigmoidf_(v);
+  return v;
+}
+
+// Generic segmented gather-accumulate.
+//   out[o, :] (+)= sum_{gi < G} sum_{e in ptr[gi*seg_stride + o] .. ptr[gi*seg_stride + o + 1]}
+//                       w(e) * src[(gi*src_group_rows + idx[e]), :]
+// forward : G=1, ptr=csr_rowptr, idx=csr_col, src=X,  o over R*n_rows, weight index = e
+// backward: G=R, ptr=csc_rowptr, idx=csc_row, src=dS, o over N,        weight index = perm[e]
+template <int LPR, int CH, int U, int MODE, bool USE_PERM>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    gather_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                       const int32_t* __restrict__ perm, const float* __restrict__ vals,
+                       const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
+                       int G, int64_t seg_stride, int64_t src_group_rows, int nvec /* D/4 */, int accumulate) {
+  constexpr int SUBS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t warp_global = (int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t o = row_begin + warp_global * SUBS + sub;
+  if (o >= row_end) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const size_t D = (size_t)nvec * 4;
+
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int gi = 0; gi < G; ++gi) {
+    const int64_t s = (int64_t)gi * seg_stride + o;
+    const int beg = ld_stream_i32(ptr + s);
+    const int end = ld_stream_i32(ptr + s + 1);
+    const float4* __restrict__ sbase = reinterpret_cast<const float4*>(src + (size_t)gi * src_group_rows * D);
+    for (int base = beg; base < end; base += LPR) {
+      const int my_e = base + l;
+      int my_idx = 0;
+      float my_w = 0.f;
+      if (my_e < end) {
+        my_idx = ld_stream_i32(idx + my_e);
+        if (MODE != IDDGCN_VALS_ONES) my_w = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + my_e) : my_e);
+      }
+      const int cnt = (end - base < LPR) ? (end - base) : LPR;
+      for (int j = 0; j < cnt; j += U) {
+        float4 v[U][CH];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = j + u;
+          const int sidx = __shfl_sync(mask, my_idx, jj & (LPR - 1), LPR);
+          if (MODE != IDDGCN_VALS_ONES) w[u] = __shfl_sync(mask, my_w, jj & (LPR - 1), LPR);
+          const float4* rowp = sbase + (size_t)sidx * nvec;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int vi = l + c * LPR;
+            if (jj < cnt && vi < nvec) v[u][c] = __ldg(rowp + vi);
+            else v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (MODE == IDDGCN_VALS_ONES) {
+              acc[c].x += v[u][c].x; acc[c].y += v[u][c].y; acc[c].z += v[u][c].z; acc[c].w += v[u][c].w;
+            } else {
+              acc[c].x = fmaf(w[u], v[u][c].x, acc[c].x); acc[c].y = fmaf(w[u], v[u][c].y, acc[c].y);
+              acc[c].z = fmaf(w[u], v[u][c].z, acc[c].z); acc[c].w = fmaf(w[u], v[u][c].w, acc[c].w);
+            }
+          }
+        }
+      }
+    }
+  }
+  float4* orow = reinterpret_cast<float4*>(out + (size_t)o * D);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vi = l + c * LPR;
+    if (vi < nvec) {
+      float4 r = acc[c];
+      if (accumulate) {
+        const float4 prev = orow[vi];
+        r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+      }
+      st_stream_f4(orow + vi, r);
+    }
+  }
+}
+
+// SDDMM: dvals[e] = <dS[seg(e), :], X[col[e], :]> (· σ'(vals[e]) in SIGMOID mode), CSR edge order.
+template <int LPR, int CH, int U, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    sddmm_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ vals,
+                      const float* __restrict__ dS, const float* __restrict__ X, float* __restrict__ dvals,
+                      int64_t num_rows, int nvec) {
+  constexpr int SUBS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t warp_global = (int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t o = warp_global * SUBS + sub;
+  if (o >= num_rows) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int beg = ld_stream_i32(ptr + o);
+  const int end = ld_stream_i32(ptr + o + 1);
+  if (beg >= end) return;
+  const float4* __restrict__ grow = reinterpret_cast<const float4*>(dS) + (size_t)o * nvec;
+  const float4* __restrict__ xb = reinterpret_cast<const float4*>(X);
+  float4 g[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vi = l + c * LPR;
+    g[c] = (vi < nvec) ? ld_stream_f4(grow + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int base = beg; base < end; base += LPR) {
+    const int my_e = base + l;
+    const int my_idx = (my_e < end) ? ld_stream_i32(idx + my_e) : 0;
+    const int cnt = (end - base < LPR) ? (end - base) : LPR;
+    float my_out = 0.f;
+    for (int j = 0; j < cnt; j += U) {
+      float4 v[U][CH];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j + u;
+        const int sidx = __shfl_sync(mask, my_idx, jj & (LPR - 1), LPR);
+        const float4* rowp = xb + (size_t)sidx * nvec;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int vi = l + c * LPR;
+          if (jj < cnt && vi < nvec) v[u][c] = __ldg(rowp + vi);
+          else v[u][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float p = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          p = fmaf(g[c].x, v[u][c].x, p); p = fmaf(g[c].y, v[u][c].y, p);
+          p = fmaf(g[c].z, v[u][c].z, p); p = fmaf(g[c].w, v[u][c].w, p);
+        }
+#pragma unroll
+        for (int off = LPR / 2; off > 0; off >>= 1) p += __shfl_xor_sync(mask, p, off, LPR);
+        if (l == j + u) my_out = p;  // lane l keeps the result of edge base+l
+      }
+    }
+    if (my_e < end) {
+      float r = my_out;
+      if (MODE == IDDGCN_VALS_SIGMOID) {
+        const float sg = sigmoidf_(__ldg(vals + my_e));
+        r *= sg * (1.0f - sg);
+      }
+      dvals[my_e] = r;
+    }
+  }
+}
+
+// one block per relation, fixed-order reduction
+template <int MODE>
+__global__ void __launch_bounds__(256) edge_value_sums_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
+                                                              const float* __restrict__ vals,
+                                                              float* __restrict__ out) {
+  __shared__ float s_part[256];
+  const int r = blockIdx.x;
+  const int beg = rowptr[(int64_t)r * n_rows], end = rowptr[(int64_t)(r + 1) * n_rows];
+  float acc = 0.f;
+  for (int e = beg + threadIdx.x; e < end; e += 256) acc += edge_weight<MODE>(vals, e);
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[r] = s_part[0];
+}
+
+// ---------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------
+struct GatherArgs {
+  const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
+  int64_t row_begin, row_end; int G; int64_t seg_stride, src_group_rows; int nvec; int accumulate;
+};
+
+template <int LPR, int CH, int U, bool USE_PERM>
+static int launch_gather_mode(const GatherArgs& a, int mode, cudaStream_t st) {
+  const int64_t rows = a.row_end - a.row_begin;
+  if (rows <= 0) return IDDGCN_OK;
+  constexpr int rows_per_block = (SPMM_THREADS / 32) * (32 / LPR);
+  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
+#define IDD_GATHER(MODE_)                                                                                        \
+  gather_rows_kernel<LPR, CH, U, MODE_, USE_PERM><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(                    \
+      a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.G, a.seg_stride, a.src_group_rows,  \
+      a.nvec, a.accumulate)
+  if (mode == IDDGCN_VALS_ONES) IDD_GATHER(IDDGCN_VALS_ONES);
+  else if (mode == IDDGCN_VALS_EXPLICIT) IDD_GATHER(IDDGCN_VALS_EXPLICIT);
+  else IDD_GATHER(IDDGCN_VALS_SIGMOID);
+#undef IDD_GATHER
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+template <bool USE_PERM>
+static int launch_gather(const GatherArgs& a, int mode, cudaStream_t st) {
+  const int nvec = a.nvec;
+  if (nvec <= 8) return launch_gather_mode<8, 1, 8, USE_PERM>(a, mode, st);
+  if (nvec <= 16) return launch_gather_mode<16, 1, 8, USE_PERM>(a, mode, st);
+  if (nvec <= 32) return launch_gather_mode<32, 1, 8, USE_PERM>(a, mode, st);
+  if (nvec <= 64) return launch_gather_mode<32, 2, 4, USE_PERM>(a, mode, st);
+  if (nvec <= 128) return launch_gather_mode<32, 4, 2, USE_PERM>(a, mode, st);
+  set_error("feature width D=%d > 512 is not supported", nvec * 4);
+  return IDDGCN_ELIMIT;
+}
+
+template <int LPR, int CH, int U>
+static int launch_sddmm_mode(const iddgcn_graph* g, const float* dS, const float* X, const float* vals, int mode,
+                             float* dvals, int nvec, cudaStream_t st) {
+  const int64_t rows = (int64_t)g->R * g->n_rows;
+  constexpr int rows_per_block = (SPMM_THREADS / 32) * (32 / LPR);
+  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
+  if (mode == IDDGCN_VALS_SIGMOID)
+    sddmm_rows_kernel<LPR, CH, U, IDDGCN_VALS_SIGMOID><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
+        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec);
+  else
+    sddmm_rows_kernel<LPR, CH, U, IDDGCN_VALS_EXPLICIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
+        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+static int check_common(const iddgcn_graph* g, int64_t D, const float* vals, int mode) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  IDD_CHECK(D > 0 && (D % 4) == 0, IDDGCN_EINVAL, "feature width D=%lld must be a positive multiple of 4",
+            (long long)D);
+  IDD_CHECK(mode >= IDDGCN_VALS_ONES && mode <= IDDGCN_VALS_SIGMOID, IDDGCN_EINVAL, "bad vals_mode %d", mode);
+  IDD_CHECK(mode == IDDGCN_VALS_ONES || vals != nullptr || g->nnz == 0, IDDGCN_EINVAL,
+            "vals is NULL but vals_mode=%d", mode);
+  return IDDGCN_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
+                   int64_t row_begin, int64_t row_end, cudaStream_t st) {
+  GatherArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, 1, 0, 0, (int)(D / 4), 0};
+  return launch_gather<false>(a, mode, st);
+}
+
+int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
+                     int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st) {
+  GatherArgs a{g->csc_rowptr, g->csc_row, g->csc_perm, vals, dS, dX, row_begin, row_end, g->R, g->N, g->n_rows,
+               (int)(D / 4), accumulate};
+  return launch_gather<true>(a, mode, st);
+}
+
+}  // namespace iddgcn
+
+using namespace iddgcn;
+
+extern "C" {
+
+int iddgcn_spmm_fwd(const iddgcn_graph_t* g, const float* X, int64_t D, const float* vals, int vals_mode, float* S,
+                    void* stream) {
+  IDD_TRY(check_common(g, D, vals, vals_mode));
+  IDD_CHECK(X && S, IDDGCN_EINVAL, "X or S is NULL");
+  IDD_CHECK(aligned16(X) && aligned16(S), IDDGCN_EINVAL, "X and S must be 16-byte aligned");
+  return spmm_fwd_range(g, X, D, vals, vals_mode, S, 0, (int64_t)g->R * g->n_rows, (cudaStream_t)stream);
+}
+
+int iddgcn_spmm_bwd_x(const iddgcn_graph_t* g, const float* dS, int64_t D, const float* vals, int vals_mode,
+                      float* dX, int accumulate, void* stream) {
+  IDD_TRY(check_common(g, D, vals, vals_mode));
+  IDD_CHECK(dS && dX, IDDGCN_EINVAL, "dS or dX is NULL");
+  IDD_CHECK(aligned16(dS) && aligned16(dX), IDDGCN_EINVAL, "dS and dX must be 16-byte aligned");
+  return spmm_bwd_x_range(g, dS, D, vals, vals_mode, dX, accumulate, 0, g->N, (cudaStream_t)stream);
+}
+
+int iddgcn_spmm_bwd_vals(const iddgcn_graph_t* g, const float* dS, const float* X, int64_t D, const float* vals,
+                         int vals_mode, float* dvals, void* stream) {
+  IDD_TRY(check_common(g, D, vals, vals_mode));
+  IDD_CHECK(dS && X && dvals, IDDGCN_EINVAL, "dS, X or dvals is NULL");
+  IDD_CHECK(aligned16(dS) && aligned16(X), IDDGCN_EINVAL, "dS and X must be 16-byte aligned");
+  if (g->nnz == 0) return IDDGCN_OK;
+  const int nvec = (int)(D / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
+  if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
+  if (nvec <= 32) return launch_sddmm_mode<32, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
+  if (nvec <= 64) return launch_sddmm_mode<32, 2, 4>(g, dS, X, vals, vals_mode, dvals, nvec, st);
+  if (nvec <= 128) return launch_sddmm_mode<32, 4, 2>(g, dS, X, vals, vals_mode, dvals, nvec, st);
+  set_error("feature width D=%lld > 512 is not supported", (long long)D);
+  return IDDGCN_ELIMIT;
+}
+
+int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_mode, float* out_per_rel,
+                           void* stream) {
+  IDD_CHECK(g != nullptr && out_per_rel != nullptr, IDDGCN_EINVAL, "graph or out is NULL");
+  IDD_CHECK(vals_mode >= IDDGCN_VALS_ONES && vals_mode <= IDDGCN_VALS_SIGMOID, IDDGCN_EINVAL, "bad vals_mode");
+  IDD_CHECK(vals_mode == IDDGCN_VALS_ONES || vals != nullptr || g->nnz == 0, IDDGCN_EINVAL, "vals is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vals_mode == IDDGCN_VALS_ONES)
+    edge_value_sums_kernel<IDDGCN_VALS_ONES><<<g->R, 256, 0, st>>>(g->csr_rowptr, g->n_rows, vals, out_per_rel);
+  else if (vals_mode == IDDGCN_VALS_EXPLICIT)
+    edge_value_sums_kernel<IDDGCN_VALS_EXPLICIT><<<g->R, 256, 0, st>>>(g->csr_rowptr, g->n_rows, vals, out_per_rel);
+  else
+    edge_value_sums_kernel<IDDGCN_VALS_SIGMOID><<<g->R, 256, 0, st>>>(g->csr_rowptr, g->n_rows, vals, out_per_rel);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---- host-buffer end-to-end path ------------------------------------------------------------
+int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const float* dS_host, int64_t D,
+                             float* S_host, float* dX_host) {
+  IDD_TRY(check_common(g, D, nullptr, IDDGCN_VALS_ONES));
+  IDD_CHECK(X_host && dS_host, IDDGCN_EINVAL, "X_host or dS_host is NULL");
+  const size_t xN = (size_t)g->N * D, sN = (size_t)g->R * g->n_rows * D;
+  DevBuf<float> dX_in, dS_in, dS_out, dX_out;
+  IDD_CUDA(dX_in.ensure(xN)); IDD_CUDA(dS_in.ensure(sN)); IDD_CUDA(dS_out.ensure(sN)); IDD_CUDA(dX_out.ensure(xN));
+  cudaStream_t s_in, s_cmp, s_out;
+  IDD_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  IDD_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+  IDD_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  cudaEvent_t ev_x, ev_ds, ev_chunk;
+  IDD_CUDA(cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming));
+  IDD_CUDA(cudaEventCreateWithFlags(&ev_ds, cudaEventDisableTiming));
+  IDD_CUDA(cudaEventCreateWithFlags(&ev_chunk, cudaEventDisableTiming));
+  int rc = IDDGCN_OK;
+  auto body = [&]() -> int {
+    constexpr int NCHUNK = 8;
+    IDD_CUDA(cudaMemcpyAsync(dX_in.p, X_host, xN * 4, cudaMemcpyHostToDevice, s_in));
+    IDD_CUDA(cudaEventRecord(ev_x, s_in));
+    IDD_CUDA(cudaMemcpyAsync(dS_in.p, dS_host, sN * 4, cudaMemcpyHostToDevice, s_in));
+    IDD_CUDA(cudaEventRecord(ev_ds, s_in));
+    IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev_x, 0));
+    const int64_t srows = (int64_t)g->R * g->n_rows;
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int64_t lo = srows * c / NCHUNK, hi = srows * (c + 1) / NCHUNK;
+      IDD_TRY(spmm_fwd_range(g, dX_in.p, D, nullptr, IDDGCN_VALS_ONES, dS_out.p, lo, hi, s_cmp));
+      if (S_host && hi > lo) {
+        IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
+        IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
+        IDD_CUDA(cudaMemcpyAsync(S_host + (size_t)lo * D, dS_out.p + (size_t)lo * D, (size_t)(hi - lo) * D * 4,
+                                 cudaMemcpyDeviceToHost, s_out));
+      }
+    }
+    IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev_ds, 0));
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int64_t lo = g->N * c / NCHUNK, hi = g->N * (c + 1) / NCHUNK;
+      IDD_TRY(spmm_bwd_x_range(g, dS_in.p, D, nullptr, IDDGCN_VALS_ONES, dX_out.p, 0, lo, hi, s_cmp));
+      if (dX_host && hi > lo) {
+        IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
+        IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
+        IDD_CUDA(cudaMemcpyAsync(dX_host + (size_t)lo * D, dX_out.p + (size_t)lo * D, (size_t)(hi - lo) * D * 4,
+                                 cudaMemcpyDeviceToHost, s_out));
+      }
+    }
+    IDD_CUDA(cudaStreamSynchronize(s_cmp));
+    IDD_CUDA(cudaStreamSynchronize(s_out));
+    IDD_CUDA(cudaStreamSynchronize(s_in));
+    return IDDGCN_OK;
+  };
+  rc = body();
+  cudaDeviceSynchronize();
+  cudaEventDestroy(ev_x); cudaEventDestroy(ev_ds); cudaEventDestroy(ev_chunk);
+  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
+  return rc;
+}
+
+// ---- DLPack flavour ------------------------------------------------------------------------
+// dlpack.h (v0.x) ABI, restated so that no third-party header is needed.
+typedef struct { int32_t device_type; int32_t device_id; } idd_DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } idd_DLDataType;
+typedef struct {
+  void* data; idd_DLDevice device; int32_t ndim; idd_DLDataType dtype; int64_t* shape; int64_t* strides;
+  uint64_t byte_offset;
+} idd_DLTensor;
+typedef struct idd_DLManagedTensor {
+  idd_DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct idd_DLManagedTensor*);
+} idd_DLManagedTensor;
+
+static int dl_f32_cuda(void* capsule_ptr, const char* name, int device, float** data, int64_t* numel,
+                       int64_t* last_dim) {
+  IDD_CHECK(capsule_ptr != nullptr, IDDGCN_EINVAL, "%s: NULL DLManagedTensor", name);
+  const idd_DLTensor& t = reinterpret_cast<idd_DLManagedTensor*>(capsule_ptr)->dl_tensor;
+  IDD_CHECK(t.device.device_type == 2 /*kDLCUDA*/, IDDGCN_EINVAL,
+            "%s: DLPack tensor is not on a CUDA device (device_type=%d); there is no CPU path", name,
+            t.device.device_type);
+  IDD_CHECK(t.device.device_id == device, IDDGCN_EINVAL, "%s: tensor on cuda:%d but handle on cuda:%d", name,
+            t.device.device_id, device);
+  IDD_CHECK(t.dtype.code == 2 && t.dtype.bits == 32 && t.dtype.lanes == 1, IDDGCN_EINVAL, "%s: dtype must be float32",
+            name);
+  IDD_CHECK(t.ndim >= 1, IDDGCN_EINVAL, "%s: ndim must be >= 1", name);
+  int64_t n = 1;
+  for (int i = 0; i < t.ndim; ++i) n *= t.shape[i];
+  if (t.strides) {
+    int64_t expect = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+      IDD_CHECK(t.shape[i] == 1 || t.strides[i] == expect, IDDGCN_EINVAL, "%s: tensor must be compact row-major",
+                name);
+      expect *= t.shape[i];
+    }
+  }
+  *data = reinterpret_cast<float*>(reinterpret_cast<char*>(t.data) + t.byte_offset);
+  *numel = n;
+  *last_dim = t.shape[t.ndim - 1];
+  return IDDGCN_OK;
+}
+
+int iddgcn_spmm_fwd_dl(const iddgcn_graph_t* g, void* X_dl, void* vals_dl, int vals_mode, void* S_dl, void* stream) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  float *X, *S, *vals = nullptr;
+  int64_t nx, ns, nv, dx, ds, dv;
+  IDD_TRY(dl_f32_cuda(X_dl, "X", g->device, &X, &nx, &dx));
+  IDD_TRY(dl_f32_cuda(S_dl, "S", g->device, &S, &ns, &ds));
+  IDD_CHECK(dx == ds, IDDGCN_EINVAL, "X and S disagree on the feature width (%lld vs %lld)", (long long)dx,
+            (long long)ds);
+  IDD_CHECK(nx == g->N * dx, IDDGCN_EINVAL, "X must be [N=%lld, D]", (long long)g->N);
+  IDD_CHECK(ns == (int64_t)g->R * g->n_rows * dx, IDDGCN_EINVAL, "S must be [R, n_rows, D]");
+  if (vals_dl) {
+    IDD_TRY(dl_f32_cuda(vals_dl, "vals", g->device, &vals, &nv, &dv));
+    IDD_CHECK(nv == g->nnz, IDDGCN_EINVAL, "vals must have nnz=%lld elements", (long long)g->nnz);
+  }
+  return iddgcn_spmm_fwd(g, X, dx, vals, vals_mode, S, stream);
+}
+
+int iddgcn_spmm_bwd_x_dl(const iddgcn_graph_t* g, void* dS_dl, void* vals_dl, int vals_mode, void* dX_dl,
+                         int accumulate, void* stream) {
+  IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
+  float *dS, *dX, *vals = nullptr;
+  int64_t nx, ns, nv, dx, ds, dv;
+  IDD_TRY(dl_f32_cuda(dS_dl, "dS", g->device, &dS, &ns, &ds));
+  IDD_TRY(dl_f32_cuda(dX_dl, "dX", g->device, &dX, &nx, &dx));
+  IDD_CHECK(dx == ds, IDDGCN_EINVAL, "dS and dX disagree on the feature width");
+  IDD_CHECK(nx == g->N * dx, IDDGCN_EINVAL, "dX must be [N=%lld, D]", (long long)g->N);
+  IDD_CHECK(ns == (int64_t)g->R * g->n_rows * dx, IDDGCN_EINVAL, "dS must be [R, n_rows, D]");
+  if (vals_dl) {
+    IDD_TRY(dl_f32_cuda(vals_dl, "vals", g->device, &vals, &nv, &dv));
+    IDD_CHECK(nv == g->nnz, IDDGCN_EINVAL, "vals must have nnz=%lld elements", (long long)g->nnz);
+  }
+  return iddgcn_spmm_bwd_x(g, dS, dx, vals, vals_mode, dX, accumulate, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+/*
+ * iddgcn.h — C ABI of libiddgcn_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the relational directed graph-convolution hot path of
+ * AhauBioinformatics/IDDGCN.  The reference has no FFI of its own: the seam is
+ * its Keras-layer Python API, which executes stock TensorFlow ops.  Each entry
+ * point below names the reference call site (file:line under the reference
+ * tree) whose arithmetic it replaces.  The Python host layer
+ * (iddgcn_b200 package) binds these through ctypes and re-exposes the reference's
+ * own names (get_adj_mats, IDDGCN_Layer, DistMult, get_IDDGCN_Model).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative IDDGCN_E* code on error;
+ *     iddgcn_last_error() returns a thread-local message for the last failure.
+ *   - all tensor arguments are plain pointers + sizes; unless a name ends in
+ *     `_host`, pointers are DEVICE pointers on the handle's device, row-major,
+ *     contiguous, caller-owned.  The library never returns memory the caller
+ *     must free except through the opaque handles (create/destroy pairs).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls are asynchronous on that stream unless stated otherwise.
+ *   - handles are bound to the device that was current at creation and are not
+ *     thread-safe; the library is re-entrant across handles.
+ *   - there is NO CPU fallback: with no CUDA device every compute entry point
+ *     returns IDDGCN_ECUDA.
+ *   - integer outputs (CSR/CSC) are bit-exact w.r.t. the reference semantics;
+ *     fp32 kernels accumulate in fp32 with a fixed, atomics-free order, so
+ *     results are run-to-run reproducible.
+ */
+#ifndef IDDGCN_H_
+#define IDDGCN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDDGCN_OK        0
+#define IDDGCN_EINVAL   -1   /* bad argument (shape, range, NULL)            */
+#define IDDGCN_ECUDA    -2   /* CUDA runtime error / no device               */
+#define IDDGCN_ENOMEM   -3   /* device or host allocation failed             */
+#define IDDGCN_ERANGE   -4   /* entity index outside [0, num_entities)       */
+#define IDDGCN_ELIMIT   -5   /* size exceeds an implementation limit (int32) */
+
+/* edge-value modes shared by the SpMM family */
+#define IDDGCN_VALS_ONES     0   /* a_e = 1.0 (utils1.py:439)                              */
+#define IDDGCN_VALS_EXPLICIT 1   /* a_e = vals[e]              (explaiNE.py:86 watches adj.values) */
+#define IDDGCN_VALS_SIGMOID  2   /* a_e = sigmoid(vals[e])     (GnnExplainer.py:33, IDDGCN_explain.py:52) */
+
+typedef struct iddgcn_graph iddgcn_graph_t;
+typedef struct iddgcn_model iddgcn_model_t;
+typedef struct iddgcn_plan  iddgcn_plan_t;
+
+const char* iddgcn_last_error(void);
+/* library / build identification: "iddgcn_b200 <ver> sm_100a" */
+const char* iddgcn_version(void);
+/* number of kernel launches issued by this library on the calling thread's
+ * handles since process start (bench.py's gpu_launches). */
+int64_t iddgcn_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Graph construction — replaces utils1.get_adj_mats + distinct
+ * (prediction/utils1.py:415-451): per relation i keep triples with rel==i,
+ * take (head,tail), np.unique(axis=0) (lexicographic sort + dedup), values 1.
+ * Built entirely on device: pack (rel,head,tail) keys -> LSD radix sort ->
+ * unique -> relation-segmented CSR; then (rel,tail,head) sort -> CSC plus the
+ * CSC->CSR edge permutation.
+ *
+ *   triples      int64 [M,3] rows (head, rel, tail)  (IDDGCN.py:368 passes X_train.values)
+ *   triples_on_device  0: host pointer, 1: device pointer
+ *   num_entities N  = number of source nodes (columns)
+ *   row_lo,row_hi   destination-row block kept by this handle: triples whose
+ *                   head is outside [row_lo,row_hi) are dropped (row-block
+ *                   partition for multi-GPU; pass 0,N for the whole graph)
+ *   Triples whose rel is outside [0,R) are ignored (the reference's boolean
+ *   filter utils1.py:425 never selects them); head/tail outside [0,N) ->
+ *   IDDGCN_ERANGE.  Synchronises the stream before returning (nnz is needed
+ *   on the host).
+ * Layout produced (all int32, device):
+ *   csr_rowptr [R*n_rows+1]  segment s = r*n_rows + (head-row_lo)
+ *   csr_col    [nnz]         tail of each edge, ascending within a segment
+ *   csr_row    [nnz]         local head (head-row_lo) of each edge
+ *   csc_rowptr [R*N+1]       segment s = r*N + tail
+ *   csc_row    [nnz]         local head of each in-edge, ascending within a segment
+ *   csc_perm   [nnz]         CSR edge id of each CSC entry
+ * ------------------------------------------------------------------------ */
+int iddgcn_graph_build(const int64_t* triples, int64_t M, int triples_on_device,
+                       int64_t num_entities, int num_relations,
+                       int64_t row_lo, int64_t row_hi,
+                       void* stream, iddgcn_graph_t** out);
+int iddgcn_graph_destroy(iddgcn_graph_t* g);
+/* nnz_per_rel may be NULL, else int64[R] */
+int iddgcn_graph_info(const iddgcn_graph_t* g, int64_t* num_entities, int* num_relations,
+                      int64_t* n_rows, int64_t* row_lo, int64_t* nnz, int64_t* nnz_per_rel);
+/* copy the integer structure to HOST buffers (any pointer may be NULL). Blocking. */
+int iddgcn_graph_export_host(const iddgcn_graph_t* g,
+                             int32_t* csr_rowptr, int32_t* csr_col, int32_t* csr_row,
+                             int32_t* csc_rowptr, int32_t* csc_row, int32_t* csc_perm);
+/* borrow the device arrays (valid until destroy) — for zero-copy wrapping as tensors */
+int iddgcn_graph_device_ptrs(const iddgcn_graph_t* g,
+                             const int32_t** csr_rowptr, const int32_t** csr_col, const int32_t** csr_row,
+                             const int32_t** csc_rowptr, const int32_t** csc_row, const int32_t** csc_perm);
+
+/* ------------------------------------------------------------------------
+ * Relational SpMM family — replaces tf.sparse.sparse_dense_matmul(adj_i, embeddings)
+ * (prediction/IDDGCN.py:70) for all relations in ONE launch, and its TF
+ * gradient (sparse_grad._SparseTensorDenseMatMulGrad; used through
+ * IDDGCN.py:172, explaiNE.py:17, GnnExplainer.py:51, IDDGCN_explain.py:84).
+ *
+ *   X   [N, D]           source features           (fp32, D % 4 == 0, 16-byte aligned)
+ *   S   [R, n_rows, D]   S_r = A_r · X
+ *   dS  [R, n_rows, D]
+ *   dX  [N, D]           dX = Σ_r A_rᵀ · dS_r      (accumulate!=0: dX += ...)
+ *   vals [nnz]           per-edge values / mask logits in CSR edge order, or NULL
+ *   dvals [nnz]          ∂L/∂vals[e]: mode EXPLICIT/ONES: <dS[row_e], X[col_e]>;
+ *                        mode SIGMOID: that · σ(v)(1-σ(v))   (SparseDenseCwiseMul grad)
+ * Per-edge weights are applied in registers and never materialised in HBM.
+ * Sum order inside a row is ascending column (TF-CPU order)
+ * per lane; no atomics anywhere.
+ * ------------------------------------------------------------------------ */
+int iddgcn_spmm_fwd(const iddgcn_graph_t* g, const float* X, int64_t D,
+                    const float* vals, int vals_mode, float* S, void* stream);
+int iddgcn_spmm_bwd_x(const iddgcn_graph_t* g, const float* dS, int64_t D,
+                      const float* vals, int vals_mode, float* dX, int accumulate, void* stream);
+int iddgcn_spmm_bwd_vals(const iddgcn_graph_t* g, const float* dS, const float* X, int64_t D,
+                         const float* vals, int vals_mode, float* dvals, void* stream);
+/* Σ_e a_e per relation -> out[R] (structure_loss counts, IDDGCN_explain.py:31-34) */
+int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_mode,
+                           float* out_per_rel, void* stream);
+
+/* End-to-end variant with HOST buffers (pinned or pageable): uploads X and dS,
+ * runs fwd + bwd_x, downloads S and dX; copies are chunked and overlapped with
+ * the kernels on internal streams.  Blocking.  Any of S_host/dX_host may be
+ * NULL to skip that download. */
+int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const float* dS_host,
+                             int64_t D, float* S_host, float* dX_host);
+
+/* DLPack flavour of the two hot entry points: arguments are DLManagedTensor*
+ * (dlpack.h v0.x ABI, as produced by tensor.__dlpack__()); dtype float32,
+ * device kDLCUDA matching the handle, compact row-major.  The capsules stay
+ * owned by the caller (the library never calls the deleter). */
+int iddgcn_spmm_fwd_dl(const iddgcn_graph_t* g, void* X_dl, void* vals_dl, int vals_mode,
+                       void* S_dl, void* stream);
+int iddgcn_spmm_bwd_x_dl(const iddgcn_graph_t* g, void* dS_dl, void* vals_dl, int vals_mode,
+                         void* dX_dl, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Triple plan — the per-call index structure the triple stage needs:
+ * head/rel/tail as int32 plus the permutations that sort triples by head and
+ * by tail, so that every gather's backward (tf.nn.embedding_lookup grad =
+ * UnsortedSegmentSum, IDDGCN.py:71-72,226-227) is an atomics-free segment sum.
+ *   head, rel, tail   int64 [T] (device if on_device else host)
+ * ------------------------------------------------------------------------ */
+int iddgcn_plan_create(const int64_t* head, const int64_t* rel, const int64_t* tail, int64_t T,
+                       int on_device, int64_t num_entities, int num_relations,
+                       void* stream, iddgcn_plan_t** out);
+int iddgcn_plan_destroy(iddgcn_plan_t* p);
+
+/* ------------------------------------------------------------------------
+ * Layer-level operators (IDDGCN_Layer.call, prediction/IDDGCN.py:60-79).
+ *
+ * iddgcn_relation_transform: Z[r] = S[r] · W[r]  ([R,N,D]·[R,D,D]) — the
+ *   per-relation transform hoisted from the T gathered rows (IDDGCN.py:76-77)
+ *   to the N aggregated rows; same dot products, same values.
+ * iddgcn_layer_fwd: for every triple k
+ *     alpha = softmax(Hin[k]·W_alpha + b_alpha); gate_i = sigmoid(alpha_i)   (:66,:75)
+ *     P_H = Hin[k]·W_self + Σ_i gate_i · Z_i[head_k]                          (:62,:76)
+ *     P_T = Tin[k]·W_self + Σ_i gate_i · Z_i[tail_k]                          (:63,:77)
+ *     Hout = sigmoid(P_H), Tout = sigmoid(P_T)                                (:79)
+ *   Hin/Tin may be NULL: then they are gathered from `emb` rows head_k / tail_k
+ *   (the Embedding lookups, IDDGCN.py:226-227).  alpha_out [T,R] is saved for
+ *   the backward pass (may be NULL for inference).
+ * iddgcn_layer_bwd: given dHout,dTout produces
+ *     dPH,dPT [T,D] (pre-activation grads), dz [T,R] (softmax-logit grads),
+ *     dHin,dTin [T,D] (if Hin given; else they are segment-summed into demb),
+ *   SURVEY App. A eq. 5-9.
+ * ------------------------------------------------------------------------ */
+int iddgcn_relation_transform(const float* S, const float* W, int R, int64_t N, int64_t D,
+                              float* Z, void* stream);
+int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb,
+                     const float* Hin, const float* Tin, const float* Z,
+                     const float* W_self, const float* W_alpha, const float* b_alpha,
+                     int64_t D, float* Hout, float* Tout, float* alpha_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Whole-model handle — get_IDDGCN_Model (IDDGCN.py:201-285): Embedding(N,D),
+ * three IDDGCN_Layer all fed the raw embedding table, DistMult decoder
+ * (IDDGCN.py:82-109); IDDGCN_Model.train_step (IDDGCN.py:123-178): positive +
+ * negative forward, BinaryCrossentropy (clip 1e-7) · 1/N, backward, Keras Adam.
+ *
+ * Parameters live in ONE flat fp32 device buffer in Keras trainable_weights
+ * order (so Adam is a single fused launch and .h5 I/O is a slice table):
+ *   entity_embeddings [N,D];
+ *   per layer l=0..L-1: relation_kernels [R,D,D], self_kernel [D,D],
+ *                       relation_weights [R] (unused by call, IDDGCN.py:39-44),
+ *                       W_alpha [D,R], b_alpha [R];
+ *   DistMult rel_embedding [R,D].
+ * ------------------------------------------------------------------------ */
+int iddgcn_model_create(int64_t num_entities, int num_relations, int64_t dim, int num_layers,
+                        iddgcn_model_t** out);
+int iddgcn_model_destroy(iddgcn_model_t* m);
+int64_t iddgcn_model_num_params(const iddgcn_model_t* m);
+/* device pointer to the flat parameter buffer / its gradient / Adam moments */
+int iddgcn_model_buffers(iddgcn_model_t* m, float** params, float** grads, float** adam_m, float** adam_v);
+/* y [T] = model(head, rel, tail | graph, optional edge vals)   (IDDGCN.py:147-153, IDDGCN_eval.py:97-105) */
+int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p,
+                         const float* vals, int vals_mode, float* y, void* stream);
+/* One training step (IDDGCN.py:123-178).  loss_out: DEVICE float[1] receiving the
+ * BCE mean BEFORE the 1/N scaling (what tf.print(loss) shows, :167); y_out
+ * [T_pos+T_neg] optional.  step_index t>=1 drives Adam bias correction.
+ * apply_update=0 leaves parameters untouched (gradients only). */
+int iddgcn_model_train_step(iddgcn_model_t* m, const iddgcn_graph_t* g,
+                            const iddgcn_plan_t* pos, const iddgcn_plan_t* neg,
+                            float lr, float beta1, float beta2, float eps, int64_t step_index,
+                            int apply_update, float* loss_out, float* y_out, void* stream);
+/* Backward of a scalar objective through model_forward for one plan:
+ * dy [T] is ∂L/∂y.  Accumulates parameter grads into the grads buffer
+ * (zero_grads!=0 clears it first) and, if dvals!=NULL, writes ∂L/∂vals [nnz]
+ * (explaiNE.py:17; GnnExplainer.py:51). Must follow a model_forward call with
+ * the same (g,p,vals) on the same stream. */
+int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p,
+                          const float* vals, int vals_mode, const float* dy,
+                          int zero_grads, float* dvals, void* stream);
+/* Keras Adam on an arbitrary flat buffer (OptimizerV2 Adam: lr_t = lr·sqrt(1-b2^t)/(1-b1^t),
+ * theta -= lr_t·m/(sqrt(v)+eps); IDDGCN.py:174, GnnExplainer.py:52, IDDGCN_explain.py:85) */
+int iddgcn_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n,
+                     float lr, float beta1, float beta2, float eps, int64_t step_index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDDGCN_H_ */

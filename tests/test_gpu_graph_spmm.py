@@ -1,0 +1,227 @@
+"""GPU parity: device graph construction (bit-exact) and the relational SpMM family, through the C ABI.
+
+Oracle = oracle/iddgcn_oracle.py (CPU restatement of utils1.get_adj_mats and of
+tf.sparse.sparse_dense_matmul + gradient).  Integer structure must be bit-exact; fp32 kernels must be
+within 1e-5 relative (north_star) of the fp64 oracle, measured against the magnitude of the result.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_triples, rel_err
+from oracle import iddgcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _oracle_struct(tri, N, R, lo=0, hi=None):
+    return O.csr_csc_from_adj(O.get_adj_mats(tri, N, R), N, lo, hi)
+
+
+@pytest.mark.parametrize("N,R,M,kw", [
+    (23, 3, 90, {}),
+    (845, 4, 40000, {"heavy_row": 7, "bad_rel": 11}),
+    (1000, 5, 3000, {"empty_rel": 2}),
+    (1, 1, 5, {}),
+    (70000, 2, 500000, {"heavy_row": 69999}),
+    (1 << 16, 4, 200000, {}),          # head/tail/rel fields exactly fill their bit widths
+])
+def test_graph_build_bit_exact(N, R, M, kw):
+    from iddgcn_b200.graph import Graph
+    tri = random_triples(N, R, M, seed=N + M, **kw)
+    g = Graph(tri, N, R)
+    ref = _oracle_struct(tri, N, R)
+    got = g.export()
+    assert g.nnz == ref["nnz"]
+    adj = O.get_adj_mats(tri, N, R)
+    assert g.nnz_per_rel == [0 if _is_placeholder(a) else a.nnz for a in adj]
+    for k in ("csr_rowptr", "csr_col", "csr_row", "csc_rowptr", "csc_row", "csc_perm"):
+        assert np.array_equal(got[k], ref[k]), k
+    # device-side triples give the same structure
+    g2 = Graph(torch.from_numpy(tri).cuda(), N, R)
+    got2 = g2.export()
+    for k in got:
+        assert np.array_equal(got[k], got2[k]), k
+
+
+def test_graph_build_empty_and_errors():
+    from iddgcn_b200._lib import IddgcnError
+    from iddgcn_b200.graph import Graph, get_adj_mats
+    g = Graph(np.zeros((0, 3), np.int64), 10, 2)
+    assert g.nnz == 0 and g.export()["csr_rowptr"].tolist() == [0] * 21
+    with pytest.raises(IddgcnError) as ei:
+        Graph(np.array([[0, 0, 10]], np.int64), 10, 2)
+    assert ei.value.code == -4
+    # reference placeholder for an empty relation: indices [[0,0,0]], values [0.] (utils1.py:427-429)
+    adj = get_adj_mats(np.array([[1, 0, 2], [1, 0, 2], [3, 0, 1]]), 5, 2)
+    ref = O.get_adj_mats(np.array([[1, 0, 2], [1, 0, 2], [3, 0, 1]]), 5, 2)
+    for a, b in zip(adj, ref):
+        assert np.array_equal(a.indices.cpu().numpy(), b.indices)
+        assert np.array_equal(a.values.cpu().numpy(), b.values)
+        assert a.dense_shape == b.dense_shape
+
+
+def test_graph_row_block_partition():
+    from iddgcn_b200.graph import Graph
+    N, R = 1000, 3
+    tri = random_triples(N, R, 20000, seed=5)
+    for lo, hi in [(0, 250), (250, 777), (777, 1000)]:
+        g = Graph(tri, N, R, row_block=(lo, hi))
+        ref = _oracle_struct(tri, N, R, lo, hi)
+        got = g.export()
+        assert g.n_rows == hi - lo and g.nnz == ref["nnz"]
+        for k in ("csr_rowptr", "csr_col", "csr_row", "csc_rowptr", "csc_row", "csc_perm"):
+            assert np.array_equal(got[k], ref[k]), (k, lo, hi)
+
+
+def _is_placeholder(a):
+    return a.nnz == 1 and a.values[0] == 0
+
+
+def _vals_for(adj, mode, seed):
+    """raw: float32 vector the kernels get (CSR edge order); eff: per-relation fp64 effective edge
+    values for the oracle (the reference's placeholder entry keeps its single 0.0)."""
+    if mode == 0:
+        return None, None
+    g = np.random.default_rng(seed)
+    raw = [g.standard_normal(0 if _is_placeholder(a) else a.nnz).astype(np.float32) for a in adj]
+    eff = []
+    for r_, a in zip(raw, adj):
+        e = r_.astype(np.float64)
+        if mode == 2:
+            e = O.sigmoid(e)
+        eff.append(np.zeros(1) if _is_placeholder(a) else e)
+    return np.concatenate(raw), eff
+
+
+@pytest.mark.parametrize("D", [4, 8, 32, 64, 100, 128, 256, 320])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_spmm_family_parity(D, mode):
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R, M = 777, 3, 9000
+    tri = random_triples(N, R, M, seed=D + mode, heavy_row=3, empty_rel=None if D != 64 else 1)
+    adj = O.get_adj_mats(tri, N, R)
+    g = Graph(tri, N, R)
+    rng = np.random.default_rng(D)
+    X = rng.random((N, D))
+    dS = rng.standard_normal((R, N, D))
+    raw, eff = _vals_for(adj, mode, seed=3)
+    Xd = torch.from_numpy(X.astype(np.float32)).cuda()
+    dSd = torch.from_numpy(dS.astype(np.float32)).cuda()
+    vd = torch.from_numpy(raw).cuda() if raw is not None else None
+    X32, dS32 = X.astype(np.float32).astype(np.float64), dS.astype(np.float32).astype(np.float64)
+    eff64 = eff
+    S_ref = O.spmm_fwd(adj, X32, eff64)
+    S = ops.spmm_fwd(g, Xd, vd, mode).cpu().numpy()
+    assert rel_err(S, S_ref) < TOL
+    dX_ref = O.spmm_bwd_x(adj, dS32, eff64)
+    dX = ops.spmm_bwd_x(g, dSd, vd, mode).cpu().numpy()
+    assert rel_err(dX, dX_ref) < TOL
+    # accumulate flag
+    base = torch.ones_like(Xd)
+    dX2 = ops.spmm_bwd_x(g, dSd, vd, mode, out=base.clone(), accumulate=True).cpu().numpy()
+    assert rel_err(dX2, dX_ref + 1.0) < TOL
+    # SDDMM (edge-value gradient); scale = Σ|terms| bound, since the dot products cancel
+    dv_ref = O.spmm_bwd_vals(adj, dS32, X32)
+    dv_ref = np.concatenate([d for d, a in zip(dv_ref, adj) if not _is_placeholder(a)])
+    if mode == 2:
+        s = np.concatenate([e for e, a in zip(eff64, adj) if not _is_placeholder(a)])
+        dv_ref = dv_ref * s * (1 - s)
+    dv = ops.spmm_bwd_vals(g, dSd, Xd, vd, mode).cpu().numpy()
+    assert dv.shape == dv_ref.shape
+    assert rel_err(dv, dv_ref, scale=np.abs(dS32).max() * np.abs(X32).max() * np.sqrt(D)) < TOL
+
+
+def test_spmm_reproducible_and_dlpack_and_host():
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R, D = 5000, 2, 128
+    tri = random_triples(N, R, 60000, seed=11)
+    g = Graph(tri, N, R)
+    X = torch.rand(N, D, device="cuda")
+    dS = torch.randn(R, N, D, device="cuda")
+    S1 = ops.spmm_fwd(g, X)
+    S2 = ops.spmm_fwd(g, X)
+    assert torch.equal(S1, S2)                      # atomics-free => bit-reproducible
+    S3 = torch.empty_like(S1)
+    ops.spmm_fwd_dlpack(g, X, S3)
+    assert torch.equal(S1, S3)
+    dX1 = ops.spmm_bwd_x(g, dS)
+    dX3 = torch.empty_like(dX1)
+    ops.spmm_bwd_x_dlpack(g, dS, dX3)
+    assert torch.equal(dX1, dX3)
+    Xh, dSh = X.cpu().pin_memory(), dS.cpu().pin_memory()
+    Sh = torch.empty(R, N, D).pin_memory()
+    dXh = torch.empty(N, D).pin_memory()
+    ops.spmm_fwd_bwd_host(g, Xh, dSh, Sh, dXh)
+    assert torch.equal(Sh, S1.cpu()) and torch.equal(dXh, dX1.cpu())
+    # DLPack path refuses CPU tensors loudly (no CPU fallback)
+    from iddgcn_b200._lib import IddgcnError
+    with pytest.raises(IddgcnError):
+        ops.spmm_fwd_dlpack(g, X.cpu(), S3)
+
+
+def test_spmm_autograd_matches_oracle():
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R, D = 300, 4, 64
+    tri = random_triples(N, R, 4000, seed=2)
+    adj = O.get_adj_mats(tri, N, R)
+    g = Graph(tri, N, R)
+    rng = np.random.default_rng(0)
+    X = torch.tensor(rng.random((N, D)), dtype=torch.float32, device="cuda", requires_grad=True)
+    v = torch.tensor(rng.uniform(0.5, 1.5, g.nnz), dtype=torch.float32, device="cuda", requires_grad=True)
+    w = torch.tensor(rng.standard_normal((R, N, D)), dtype=torch.float32, device="cuda")
+    S = ops.relational_spmm(g, X, v, 1)
+    (S * w).sum().backward()
+    vals = np.split(v.detach().cpu().numpy().astype(np.float64), np.cumsum(g.nnz_per_rel)[:-1])
+    dX_ref = O.spmm_bwd_x(adj, w.cpu().numpy().astype(np.float64), vals)
+    dv_ref = np.concatenate(O.spmm_bwd_vals(adj, w.cpu().numpy().astype(np.float64),
+                                            X.detach().cpu().numpy().astype(np.float64)))
+    assert rel_err(X.grad.cpu().numpy(), dX_ref) < TOL
+    assert rel_err(v.grad.cpu().numpy(), dv_ref, scale=np.abs(dv_ref).max() + 10) < TOL
+
+
+def test_large_graph_properties():
+    """Full bench-size (C3) checks through size-independent properties: linearity, adjoint identity
+    <A·X, dS> = <X, Aᵀ·dS>, row-sum identity against the CSR row pointer, sortedness of the structure."""
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R, D, per_rel = 1_000_000, 2, 128, 10_000_000
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    h = torch.randint(0, N, (R * per_rel,), device="cuda", generator=gen)
+    t = torch.randint(0, N, (R * per_rel,), device="cuda", generator=gen)
+    r = torch.arange(R, device="cuda").repeat_interleave(per_rel)
+    g = Graph(torch.stack([h, r, t], 1), N, R)
+    d = g.device_arrays()
+    # structure: keys strictly increasing inside the global (rel, head, tail) order, CSC is a permutation
+    seg = torch.repeat_interleave(torch.arange(R * N, device="cuda"),
+                                  (d["csr_rowptr"][1:] - d["csr_rowptr"][:-1]).long())
+    key = seg * N + d["csr_col"].long()
+    assert bool((key[1:] > key[:-1]).all())
+    perm = d["csc_perm"].long()
+    assert bool((torch.sort(perm).values == torch.arange(g.nnz, device="cuda")).all())
+    segc = torch.repeat_interleave(torch.arange(R * N, device="cuda"),
+                                   (d["csc_rowptr"][1:] - d["csc_rowptr"][:-1]).long())
+    # CSC entry j is CSR edge perm[j]: same (rel, tail) segment and same head
+    assert bool((segc % N == d["csr_col"].long()[perm]).all())
+    assert bool((d["csc_row"].long() == d["csr_row"].long()[perm]).all())
+    del seg, key, segc, perm
+    X = torch.rand(N, D, device="cuda")
+    ones = torch.ones(N, D, device="cuda")
+    S1 = ops.spmm_fwd(g, ones)
+    deg = (d["csr_rowptr"][1:] - d["csr_rowptr"][:-1]).float().view(R, N, 1)
+    assert torch.equal(S1, deg.expand(R, N, D))      # A·1 = out-degree, exact in fp32
+    del S1, ones
+    S = ops.spmm_fwd(g, X)
+    S2 = ops.spmm_fwd(g, 2 * X)
+    assert torch.equal(S2, 2 * S)                    # scaling by 2 is exact
+    del S2
+    dS = torch.randn(R, N, D, device="cuda")
+    dX = ops.spmm_bwd_x(g, dS)
+    lhs = (S.double() * dS.double()).sum().item()
+    rhs = (X.double() * dX.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)

@@ -1,0 +1,163 @@
+// dense.cu — fp32 SIMT GEMMs for the triple stage (see dense.cuh).
+//
+// Call sites they replace: tf.matmul(head_e, self_kernel) / tf.matmul(head_update, relation_kernel[i])
+// (prediction/IDDGCN.py:62-63,76-77) and the matmul gradients TF autodiff emits for them (IDDGCN.py:172).
+#include "dense.cuh"
+
+namespace iddgcn {
+
+constexpr int GT = 64;       // C tile is GT x GT
+constexpr int GK = 16;       // K step
+constexpr int GPAD = 4;      // keeps rows 16-byte aligned and spreads banks
+constexpr int GTHREADS = 256;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GTHREADS)
+    gemm_tile_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, int64_t strideA,
+                     const float* __restrict__ B, int64_t ldb, int64_t strideB, float* __restrict__ C, int64_t ldc,
+                     int64_t strideC, int accumulate, int64_t k_chunk, int64_t ws_split_stride) {
+  // grid: x = tile over M, y = tile over N, z = batch * splits (splits > 1 only for the split-K variant,
+  // where C points at the workspace and ws_split_stride separates the partial results).
+  __shared__ __align__(16) float As[GK][GT + GPAD];
+  __shared__ __align__(16) float Bs[GK][GT + GPAD];
+  const int splits = (k_chunk > 0 && K > 0) ? (int)((K + k_chunk - 1) / k_chunk) : 1;
+  const int b = blockIdx.z / splits;
+  const int sp = blockIdx.z % splits;
+  const int64_t k_begin = (k_chunk > 0) ? (int64_t)sp * k_chunk : 0;
+  const int64_t k_end = (k_chunk > 0) ? ((k_begin + k_chunk < K) ? k_begin + k_chunk : K) : K;
+  A += (int64_t)b * strideA;
+  B += (int64_t)b * strideB;
+  C += (int64_t)b * strideC + (int64_t)sp * ws_split_stride;
+  const int64_t m0 = (int64_t)blockIdx.x * GT, n0 = (int64_t)blockIdx.y * GT;
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += GK) {
+#pragma unroll
+    for (int i = 0; i < (GT * GK) / GTHREADS; ++i) {
+      const int idx = tid + i * GTHREADS;
+      int m, k;
+      if (TA) { m = idx % GT; k = idx / GT; } else { k = idx % GK; m = idx / GK; }
+      const int64_t gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < k_end) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (GT * GK) / GTHREADS; ++i) {
+      const int idx = tid + i * GTHREADS;
+      int n, k;
+      if (TB) { k = idx % GK; n = idx / GK; } else { n = idx % GT; k = idx / GT; }
+      const int64_t gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < k_end) v = TB ? B[gn * ldb + gk] : B[gk * ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float* c = C + gm * ldc + gn;
+      *c = accumulate ? (*c + acc[i][j]) : acc[i][j];
+    }
+  }
+}
+
+// C[b][m][n] (+)= sum_{s < splits} ws[b][s][m][n], ascending s
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
+                                     float* __restrict__ C, int64_t ldc, int64_t strideC, int accumulate) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= MN) return;
+  const float* w = ws + (int64_t)b * splits * MN + i;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += w[(int64_t)k * MN];
+  float* c = C + (int64_t)b * strideC + (i / N) * ldc + (i % N);
+  *c = accumulate ? (*c + s) : s;
+}
+
+int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA,
+             const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
+             bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
+  const int64_t gm = (M + GT - 1) / GT, gn = (N + GT - 1) / GT;
+  IDD_CHECK(gm < 0x7fffffff && gn < 65536 && batch < 65536, IDDGCN_ELIMIT, "GEMM grid too large");
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)batch);
+  const int acc = accumulate ? 1 : 0;
+  if (!transA && !transB)
+    gemm_tile_kernel<false, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+  else if (!transA && transB)
+    gemm_tile_kernel<false, true><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+  else if (transA && !transB)
+    gemm_tile_kernel<true, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+  else
+    gemm_tile_kernel<true, true><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+static void splitk_shape(int64_t M, int64_t N, int64_t K, int batch, int* splits, int64_t* k_chunk) {
+  const int64_t tiles = ((M + GT - 1) / GT) * ((N + GT - 1) / GT) * batch;
+  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;   // ~2 waves of blocks
+  int64_t max_by_k = (K + 4 * GK - 1) / (4 * GK);                  // at least 64 k per split
+  if (want > max_by_k) want = max_by_k;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  int64_t chunk = (K + want - 1) / want;
+  chunk = (chunk + GK - 1) / GK * GK;
+  if (chunk < GK) chunk = GK;
+  *k_chunk = chunk;
+  *splits = (int)((K + chunk - 1) / chunk);
+  if (*splits < 1) *splits = 1;
+}
+
+size_t gemm_tn_workspace_elems(int64_t M, int64_t N, int64_t K, int batch) {
+  int splits; int64_t chunk;
+  splitk_shape(M, N, K, batch, &splits, &chunk);
+  return (size_t)splits * (size_t)M * (size_t)N * (size_t)batch;
+}
+
+int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
+                       int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
+                       bool accumulate, float* workspace, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
+  int splits; int64_t chunk;
+  splitk_shape(M, N, K, batch, &splits, &chunk);
+  if (K <= 0) splits = 1;
+  const int64_t MN = M * N;
+  dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT), (unsigned)(batch * splits));
+  IDD_CHECK(grid.y < 65536 && grid.z < 65536, IDDGCN_ELIMIT, "split-K GEMM grid too large");
+  // partials: ws[b][s][M][N]  (strideC = splits*MN per batch, ws_split_stride = MN)
+  gemm_tile_kernel<true, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, workspace, N,
+                                                          (int64_t)splits * MN, 0, chunk, MN);
+  IDD_LAUNCH_CHECK();
+  dim3 rgrid((unsigned)((MN + 255) / 256), (unsigned)batch);
+  splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(workspace, splits, MN, N, C, ldc, strideC, accumulate ? 1 : 0);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+}  // namespace iddgcn

@@ -41,18 +41,24 @@ _SIGNATURES = {
     "iddgcn_plan_create": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, C.c_int64, C.c_int, vp, C.POINTER(vp)]),
     "iddgcn_plan_destroy": (C.c_int, [vp]),
     "iddgcn_relation_transform": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp]),
+    "iddgcn_relation_transform_bwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]),
     "iddgcn_layer_fwd": (C.c_int, [vp] * 8 + [C.c_int64, vp, vp, vp, vp]),
-    "iddgcn_layer_bwd": (C.c_int, [vp] * 11 + [C.c_int64] + [vp] * 7),
-    "iddgcn_segment_scatter": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_int, vp, C.c_int, vp]),
-    "iddgcn_distmult_fwd": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, vp]),
-    "iddgcn_distmult_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp]),
+    "iddgcn_layer_bwd": (C.c_int, [vp] * 7 + [C.c_int64, vp, vp, vp, C.c_int, vp, vp, vp, vp]),
+    "iddgcn_segment_scatter": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int, vp]),
+    "iddgcn_distmult_fwd": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
+    "iddgcn_distmult_bwd": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp]),
+    "iddgcn_bce_loss_grad": (C.c_int, [vp, C.c_int64, C.c_int64, C.c_float, vp, vp, vp]),
     "iddgcn_model_create": (C.c_int, [C.c_int64, C.c_int, C.c_int64, C.c_int, C.POINTER(vp)]),
     "iddgcn_model_destroy": (C.c_int, [vp]),
     "iddgcn_model_num_params": (C.c_int64, [vp]),
+    "iddgcn_model_param_layout": (C.c_int, [vp, c_i64p, c_i64p]),
     "iddgcn_model_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 4),
+    "iddgcn_model_release_plan": (C.c_int, [vp, vp]),
     "iddgcn_model_forward": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
     "iddgcn_model_train_step": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                           C.c_int, vp, vp, vp]),
+    "iddgcn_model_train_loop": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                          C.c_int64, vp, vp]),
     "iddgcn_model_backward": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]),
     "iddgcn_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                    vp]),

@@ -1,0 +1,564 @@
+// model.cu — whole-model handle: get_IDDGCN_Model wiring (prediction/IDDGCN.py:201-285) and
+// IDDGCN_Model.train_step (IDDGCN.py:123-178), orchestrating the kernels of spmm.cu / dense.cu / triple.cu.
+//
+// What is hoisted relative to the reference's op order (values unchanged):
+//   * S_i = A_i·E is computed ONCE per step (the reference recomputes it 3 layers x 2 calls x R times);
+//   * the per-relation transform is applied to the N aggregated rows (Z_i = S_i·W_i) instead of the T gathered
+//     rows — the same row·matrix dot products, 44x fewer of them at the shipped sizes;
+//   * head and tail sides share one (2,T,D) buffer so every self-kernel matmul is one GEMM.
+#include <unordered_map>
+#include <vector>
+#include "dense.cuh"
+#include "graph.cuh"
+#include "triple.cuh"
+
+namespace iddgcn {
+int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
+                   int64_t row_begin, int64_t row_end, cudaStream_t st);
+int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
+                     int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st);
+}  // namespace iddgcn
+
+using namespace iddgcn;
+
+struct LayerOffsets { int64_t rk, sk, rw, wa, ba; };
+struct ParamLayout {
+  int64_t emb = 0;
+  std::vector<LayerOffsets> layer;
+  int64_t rel_emb = 0;
+  int64_t total = 0;
+};
+
+struct TripleWS {
+  int64_t T = 0;
+  std::vector<float*> HT;     // L+1 buffers (2,T,D)
+  std::vector<float*> alpha;  // L buffers (T,R)
+  float* dHT[2] = {nullptr, nullptr};
+  float* dz = nullptr;
+  float* y = nullptr;
+  void release() {
+    for (float* p : HT) cudaFree(p);
+    for (float* p : alpha) cudaFree(p);
+    cudaFree(dHT[0]); cudaFree(dHT[1]); cudaFree(dz); cudaFree(y);
+    HT.clear(); alpha.clear(); dHT[0] = dHT[1] = dz = y = nullptr; T = 0;
+  }
+};
+
+struct iddgcn_model {
+  int device = 0;
+  int64_t N = 0, D = 0;
+  int R = 0, L = 0;
+  ParamLayout lay;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  int64_t* step_dev = nullptr;
+  float* loss_dev = nullptr;
+  // node-level workspace
+  float *S = nullptr, *Z = nullptr, *dZ = nullptr, *dS = nullptr;
+  DevBuf<float> gemm_ws, small_ws, y_all, dy_all;
+  std::unordered_map<const iddgcn_plan*, TripleWS> ws;
+  // captured training step
+  cudaGraphExec_t graph_exec = nullptr;
+  const void* graph_key[3] = {nullptr, nullptr, nullptr};
+  float graph_hyper[4] = {0, 0, 0, 0};
+  cudaStream_t own_stream = nullptr;
+
+  float* P(int64_t off) const { return params + off; }
+  float* G(int64_t off) const { return grads + off; }
+  size_t plane() const { return (size_t)R * N * D; }
+};
+
+static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
+
+static ParamLayout make_layout(int64_t N, int R, int64_t D, int L) {
+  ParamLayout p;
+  int64_t o = 0;
+  p.emb = o; o += pad4(N * D);
+  for (int l = 0; l < L; ++l) {
+    LayerOffsets lo;
+    lo.rk = o; o += pad4((int64_t)R * D * D);
+    lo.sk = o; o += pad4(D * D);
+    lo.rw = o; o += pad4(R);
+    lo.wa = o; o += pad4(D * R);
+    lo.ba = o; o += pad4(R);
+    p.layer.push_back(lo);
+  }
+  p.rel_emb = o; o += pad4((int64_t)R * D);
+  p.total = o;
+  return p;
+}
+
+static void model_free(iddgcn_model* m) {
+  if (!m) return;
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  for (auto& kv : m->ws) kv.second.release();
+  cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v);
+  cudaFree(m->step_dev); cudaFree(m->loss_dev);
+  cudaFree(m->S); cudaFree(m->Z); cudaFree(m->dZ); cudaFree(m->dS);
+  delete m;
+}
+
+static int ensure_triple_ws(iddgcn_model* m, const iddgcn_plan* p, TripleWS** out) {
+  TripleWS& w = m->ws[p];
+  if (w.T != p->T || w.HT.empty()) {
+    w.release();
+    const size_t td = (size_t)(p->T ? p->T : 1) * m->D;
+    const size_t tr = (size_t)(p->T ? p->T : 1) * m->R;
+    for (int l = 0; l <= m->L; ++l) {
+      float* q = nullptr;
+      IDD_CUDA(cudaMalloc((void**)&q, 2 * td * sizeof(float)));
+      w.HT.push_back(q);
+    }
+    for (int l = 0; l < m->L; ++l) {
+      float* q = nullptr;
+      IDD_CUDA(cudaMalloc((void**)&q, tr * sizeof(float)));
+      w.alpha.push_back(q);
+    }
+    IDD_CUDA(cudaMalloc((void**)&w.dHT[0], 2 * td * sizeof(float)));
+    IDD_CUDA(cudaMalloc((void**)&w.dHT[1], 2 * td * sizeof(float)));
+    IDD_CUDA(cudaMalloc((void**)&w.dz, tr * sizeof(float)));
+    IDD_CUDA(cudaMalloc((void**)&w.y, (size_t)(p->T ? p->T : 1) * sizeof(float)));
+    w.T = p->T;
+  }
+  // shared scratch sized for this plan
+  size_t gw = gemm_tn_workspace_elems(m->D, m->D, 2 * p->T, 1);
+  size_t g2 = gemm_tn_workspace_elems(m->D, m->R, p->T, 1);
+  size_t g3 = gemm_tn_workspace_elems(m->D, m->D, m->N, m->R);
+  if (g2 > gw) gw = g2;
+  if (g3 > gw) gw = g3;
+  if (gw > m->gemm_ws.n) IDD_CUDA(m->gemm_ws.ensure(gw));
+  size_t sw = colsum_scratch_elems(p->T, m->R);
+  size_t s2 = distmult_scratch_elems(p, m->D);
+  if (s2 > sw) sw = s2;
+  if (sw > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(sw));
+  *out = &w;
+  return IDDGCN_OK;
+}
+
+static int check_compat(const iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* p) {
+  IDD_CHECK(m && g && p, IDDGCN_EINVAL, "model, graph or plan is NULL");
+  IDD_CHECK(g->N == m->N && g->R == m->R && g->n_rows == m->N && g->row_lo == 0, IDDGCN_EINVAL,
+            "graph (N=%lld,R=%d,rows=%lld) does not match model (N=%lld,R=%d); the model path needs the whole graph",
+            (long long)g->N, g->R, (long long)g->n_rows, (long long)m->N, m->R);
+  IDD_CHECK(p->N == m->N && p->R == m->R, IDDGCN_EINVAL, "plan (N=%lld,R=%d) does not match model",
+            (long long)p->N, p->R);
+  return IDDGCN_OK;
+}
+
+// S = A·E and Z_l = S·W_l for every layer
+static int node_forward(iddgcn_model* m, const iddgcn_graph* g, const float* vals, int mode, cudaStream_t st) {
+  IDD_TRY(spmm_fwd_range(g, m->P(m->lay.emb), m->D, vals, mode, m->S, 0, (int64_t)m->R * m->N, st));
+  for (int l = 0; l < m->L; ++l)
+    IDD_TRY(gemm_f32(false, false, m->N, m->D, m->D, m->S, m->D, m->N * m->D, m->P(m->lay.layer[l].rk), m->D,
+                     m->D * m->D, m->Z + (size_t)l * m->plane(), m->D, m->N * m->D, m->R, false, st));
+  return IDDGCN_OK;
+}
+
+static int triple_forward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, float* y_out, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  IDD_TRY(gather_embeddings(p, m->P(m->lay.emb), m->D, w->HT[0], st));
+  for (int l = 0; l < m->L; ++l) {
+    const LayerOffsets& lo = m->lay.layer[l];
+    IDD_TRY(gemm_f32(false, false, 2 * p->T, m->D, m->D, w->HT[l], m->D, 0, m->P(lo.sk), m->D, 0, w->HT[l + 1], m->D,
+                     0, 1, false, st));
+    IDD_TRY(layer_combine(p, w->HT[l], m->Z + (size_t)l * m->plane(), m->P(lo.wa), m->P(lo.ba), m->D, w->HT[l + 1],
+                          w->alpha[l], st));
+  }
+  IDD_TRY(distmult_fwd(p, w->HT[m->L], m->P(m->lay.rel_emb), m->D, y_out, st));
+  return IDDGCN_OK;
+}
+
+// per-triple backward; accumulates into grads (sk, wa, ba, rel_emb, emb-lookup part) and into dZ
+static int triple_backward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, const float* y, const float* dy,
+                           cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  const int64_t T = p->T, D = m->D;
+  int cur = 0;
+  IDD_TRY(distmult_bwd(p, w->HT[m->L], m->P(m->lay.rel_emb), y, dy, D, w->dHT[cur], m->G(m->lay.rel_emb),
+                       m->small_ws.p, st));
+  for (int l = m->L - 1; l >= 0; --l) {
+    const LayerOffsets& lo = m->lay.layer[l];
+    const float* Zl = m->Z + (size_t)l * m->plane();
+    IDD_TRY(layer_bwd_pre(p, w->HT[l + 1], w->alpha[l], Zl, D, w->dHT[cur], w->dz, st));
+    float* dP = w->dHT[cur];
+    // dW_self = [Hin;Tin]ᵀ·dP  (eq. 8), dW_alpha = Hinᵀ·dz, db_alpha = colsum(dz)  (eq. 7)
+    IDD_TRY(gemm_tn_splitk_f32(D, D, 2 * T, w->HT[l], D, 0, dP, D, 0, m->G(lo.sk), D, 0, 1, true, m->gemm_ws.p, st));
+    IDD_TRY(gemm_tn_splitk_f32(D, m->R, T, w->HT[l], D, 0, w->dz, m->R, 0, m->G(lo.wa), m->R, 0, 1, true,
+                               m->gemm_ws.p, st));
+    IDD_TRY(colsum(w->dz, T, m->R, m->G(lo.ba), 1, m->small_ws.p, st));
+    // dZ_i += scatter(gate_i · dP)  (eq. 10)
+    IDD_TRY(segment_scatter(p, dP, w->alpha[l], D, m->dZ + (size_t)l * m->plane(), 1, st));
+    // d[Hin;Tin] = dP·W_selfᵀ (+ dz·W_alphaᵀ on the head side)  (eq. 9)
+    IDD_TRY(gemm_f32(false, true, 2 * T, D, D, dP, D, 0, m->P(lo.sk), D, 0, w->dHT[cur ^ 1], D, 0, 1, false, st));
+    IDD_TRY(layer_bwd_post(w->dz, m->P(lo.wa), T, D, m->R, w->dHT[cur ^ 1], st));
+    cur ^= 1;
+  }
+  // gradient of the two Embedding lookups (eq. 12, second and third term)
+  IDD_TRY(segment_scatter(p, w->dHT[cur], nullptr, D, m->G(m->lay.emb), 1, st));
+  return IDDGCN_OK;
+}
+
+// node-level backward: dW_i = S_iᵀ·dZ_i, dS_i = Σ_l dZ_i·W_iᵀ (eq. 11), dE += Σ_i A_iᵀ·dS_i (eq. 12), dvals (eq. 13)
+static int node_backward(iddgcn_model* m, const iddgcn_graph* g, const float* vals, int mode, float* dvals,
+                         cudaStream_t st);
+
+static int zero_step_buffers(iddgcn_model* m, bool grads_too, cudaStream_t st) {
+  if (grads_too) IDD_CUDA(cudaMemsetAsync(m->grads, 0, (size_t)m->lay.total * sizeof(float), st));
+  IDD_CUDA(cudaMemsetAsync(m->dZ, 0, (size_t)m->L * m->plane() * sizeof(float), st));
+  return IDDGCN_OK;
+}
+
+namespace iddgcn {
+int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64_t D, const float* vals, int mode,
+                   float* dvals, cudaStream_t st);
+}
+
+static int node_backward(iddgcn_model* m, const iddgcn_graph* g, const float* vals, int mode, float* dvals,
+                         cudaStream_t st) {
+  const int64_t N = m->N, D = m->D;
+  for (int l = 0; l < m->L; ++l) {
+    const LayerOffsets& lo = m->lay.layer[l];
+    float* dZl = m->dZ + (size_t)l * m->plane();
+    IDD_TRY(gemm_tn_splitk_f32(D, D, N, m->S, D, N * D, dZl, D, N * D, m->G(lo.rk), D, D * D, m->R, true,
+                               m->gemm_ws.p, st));
+    IDD_TRY(gemm_f32(false, true, N, D, D, dZl, D, N * D, m->P(lo.rk), D, D * D, m->dS, D, N * D, m->R, l > 0, st));
+  }
+  IDD_TRY(spmm_bwd_x_range(g, m->dS, D, vals, mode, m->G(m->lay.emb), 1, 0, N, st));
+  if (dvals) IDD_TRY(sddmm_dispatch(g, m->dS, m->P(m->lay.emb), D, vals, mode, dvals, st));
+  return IDDGCN_OK;
+}
+
+static int train_step_body(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* pos, const iddgcn_plan* neg,
+                           TripleWS* wp, TripleWS* wn, float lr, float b1, float b2, float eps, int64_t step,
+                           bool step_on_device, int apply_update, float* loss_out, float* y_out, cudaStream_t st) {
+  const int64_t Tp = pos->T, Tn = neg ? neg->T : 0, Tt = Tp + Tn;
+  IDD_TRY(zero_step_buffers(m, true, st));
+  IDD_TRY(node_forward(m, g, nullptr, IDDGCN_VALS_ONES, st));
+  IDD_TRY(triple_forward(m, pos, wp, m->y_all.p, st));                       // IDDGCN.py:147-153
+  if (neg) IDD_TRY(triple_forward(m, neg, wn, m->y_all.p + Tp, st));         // IDDGCN.py:154-160
+  // y_pred = concat, y_true = [1..1 | 0..0], loss = BCE; loss *= 1/N  (IDDGCN.py:161-168)
+  IDD_TRY(bce_loss_grad(m->y_all.p, Tp, Tt, 1.0f / (float)m->N, m->dy_all.p, m->loss_dev, m->small_ws.p, st));
+  IDD_TRY(triple_backward(m, pos, wp, m->y_all.p, m->dy_all.p, st));
+  if (neg) IDD_TRY(triple_backward(m, neg, wn, m->y_all.p + Tp, m->dy_all.p + Tp, st));
+  IDD_TRY(node_backward(m, g, nullptr, IDDGCN_VALS_ONES, nullptr, st));
+  if (apply_update) {
+    if (step_on_device) IDD_TRY(increment_counter(m->step_dev, st));
+    IDD_TRY(adam_apply(m->params, m->grads, m->adam_m, m->adam_v, m->lay.total, lr, b1, b2, eps, step,
+                       step_on_device ? m->step_dev : nullptr, st));          // IDDGCN.py:174
+  }
+  if (loss_out) IDD_CUDA(cudaMemcpyAsync(loss_out, m->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (y_out) IDD_CUDA(cudaMemcpyAsync(y_out, m->y_all.p, (size_t)Tt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return IDDGCN_OK;
+}
+
+static int prepare_train(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* pos, const iddgcn_plan* neg,
+                         TripleWS** wp, TripleWS** wn) {
+  IDD_TRY(check_compat(m, g, pos));
+  if (neg) IDD_TRY(check_compat(m, g, neg));
+  IDD_CHECK(pos->T + (neg ? neg->T : 0) > 0, IDDGCN_EINVAL, "train step needs at least one triple");
+  IDD_TRY(ensure_triple_ws(m, pos, wp));
+  *wn = nullptr;
+  if (neg) IDD_TRY(ensure_triple_ws(m, neg, wn));
+  const size_t Tt = (size_t)(pos->T + (neg ? neg->T : 0));
+  if (Tt > m->y_all.n) IDD_CUDA(m->y_all.ensure(Tt));
+  if (Tt > m->dy_all.n) IDD_CUDA(m->dy_all.ensure(Tt));
+  const size_t bs = bce_scratch_elems((int64_t)Tt);
+  if (bs > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(bs));
+  // ensure_triple_ws may have re-allocated the shared scratch: refresh pointers kept by callers (none are cached)
+  return IDDGCN_OK;
+}
+
+extern "C" {
+
+int iddgcn_model_create(int64_t num_entities, int num_relations, int64_t dim, int num_layers, iddgcn_model_t** out) {
+  IDD_CHECK(out != nullptr, IDDGCN_EINVAL, "out is NULL");
+  *out = nullptr;
+  IDD_CHECK(num_entities > 0 && num_relations > 0 && dim > 0 && num_layers > 0, IDDGCN_EINVAL, "sizes must be positive");
+  IDD_CHECK(num_relations <= RMAX, IDDGCN_ELIMIT, "the model path supports at most %d relations", RMAX);
+  IDD_CHECK(dim % 4 == 0 && dim <= 512, IDDGCN_ELIMIT, "embedding dim must be a multiple of 4 and <= 512");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libiddgcn_b200 has no CPU fallback");
+    return IDDGCN_ECUDA;
+  }
+  iddgcn_model* m = new iddgcn_model();
+  m->N = num_entities; m->R = num_relations; m->D = dim; m->L = num_layers;
+  m->lay = make_layout(m->N, m->R, m->D, m->L);
+  auto fail = [&](int rc) { model_free(m); return rc; };
+  auto alloc0 = [&](float** p, size_t n) -> int {
+    IDD_CUDA(cudaMalloc((void**)p, n * sizeof(float)));
+    IDD_CUDA(cudaMemset(*p, 0, n * sizeof(float)));
+    return IDDGCN_OK;
+  };
+  int rc;
+  if (cudaGetDevice(&m->device) != cudaSuccess) return fail(IDDGCN_ECUDA);
+  const size_t tot = (size_t)m->lay.total;
+  if ((rc = alloc0(&m->params, tot)) || (rc = alloc0(&m->grads, tot)) || (rc = alloc0(&m->adam_m, tot)) ||
+      (rc = alloc0(&m->adam_v, tot)) || (rc = alloc0(&m->S, m->plane())) || (rc = alloc0(&m->dS, m->plane())) ||
+      (rc = alloc0(&m->Z, m->L * m->plane())) || (rc = alloc0(&m->dZ, m->L * m->plane())) ||
+      (rc = alloc0(&m->loss_dev, 4)))
+    return fail(rc);
+  if (cudaMalloc((void**)&m->step_dev, sizeof(int64_t)) != cudaSuccess ||
+      cudaMemset(m->step_dev, 0, sizeof(int64_t)) != cudaSuccess) {
+    set_error("cudaMalloc(step counter) failed");
+    return fail(IDDGCN_ENOMEM);
+  }
+  *out = m;
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_destroy(iddgcn_model_t* m) {
+  model_free(m);
+  return IDDGCN_OK;
+}
+
+int64_t iddgcn_model_num_params(const iddgcn_model_t* m) { return m ? m->lay.total : 0; }
+
+// offsets[2+5L] (floats, into the flat buffer) in Keras weight order; sizes likewise (unpadded element counts)
+int iddgcn_model_param_layout(const iddgcn_model_t* m, int64_t* offsets, int64_t* sizes) {
+  IDD_CHECK(m && offsets && sizes, IDDGCN_EINVAL, "NULL argument");
+  int k = 0;
+  offsets[k] = m->lay.emb; sizes[k++] = m->N * m->D;
+  for (int l = 0; l < m->L; ++l) {
+    const LayerOffsets& lo = m->lay.layer[l];
+    offsets[k] = lo.rk; sizes[k++] = (int64_t)m->R * m->D * m->D;
+    offsets[k] = lo.sk; sizes[k++] = m->D * m->D;
+    offsets[k] = lo.rw; sizes[k++] = m->R;
+    offsets[k] = lo.wa; sizes[k++] = m->D * m->R;
+    offsets[k] = lo.ba; sizes[k++] = m->R;
+  }
+  offsets[k] = m->lay.rel_emb; sizes[k++] = (int64_t)m->R * m->D;
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_buffers(iddgcn_model_t* m, float** params, float** grads, float** adam_m, float** adam_v) {
+  IDD_CHECK(m != nullptr, IDDGCN_EINVAL, "model is NULL");
+  if (params) *params = m->params;
+  if (grads) *grads = m->grads;
+  if (adam_m) *adam_m = m->adam_m;
+  if (adam_v) *adam_v = m->adam_v;
+  return IDDGCN_OK;
+}
+
+// drop the cached activations of a plan (call before destroying the plan)
+int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p) {
+  IDD_CHECK(m != nullptr, IDDGCN_EINVAL, "model is NULL");
+  auto it = m->ws.find(p);
+  if (it != m->ws.end()) {
+    cudaDeviceSynchronize();
+    it->second.release();
+    m->ws.erase(it);
+  }
+  if (m->graph_exec && (m->graph_key[1] == p || m->graph_key[2] == p)) {
+    cudaGraphExecDestroy(m->graph_exec);
+    m->graph_exec = nullptr;
+  }
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, const float* vals,
+                         int vals_mode, float* y, void* stream) {
+  IDD_TRY(check_compat(m, g, p));
+  IDD_CHECK(vals_mode >= 0 && vals_mode <= 2 && (vals_mode == 0 || vals || g->nnz == 0), IDDGCN_EINVAL,
+            "bad vals / vals_mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  TripleWS* w;
+  IDD_TRY(ensure_triple_ws(m, p, &w));
+  IDD_TRY(node_forward(m, g, vals, vals_mode, st));
+  IDD_TRY(triple_forward(m, p, w, w->y, st));
+  if (y && p->T) IDD_CUDA(cudaMemcpyAsync(y, w->y, (size_t)p->T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, const float* vals,
+                          int vals_mode, const float* dy, int zero_grads, float* dvals, void* stream) {
+  IDD_TRY(check_compat(m, g, p));
+  IDD_CHECK(dy != nullptr || p->T == 0, IDDGCN_EINVAL, "dy is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = m->ws.find(p);
+  IDD_CHECK(it != m->ws.end() && it->second.T == p->T, IDDGCN_EINVAL,
+            "model_backward must follow model_forward on the same plan");
+  IDD_TRY(zero_step_buffers(m, zero_grads != 0, st));
+  IDD_TRY(triple_backward(m, p, &it->second, it->second.y, dy, st));
+  IDD_TRY(node_backward(m, g, vals, vals_mode, dvals, st));
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_train_step(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* pos,
+                            const iddgcn_plan_t* neg, float lr, float beta1, float beta2, float eps,
+                            int64_t step_index, int apply_update, float* loss_out, float* y_out, void* stream) {
+  TripleWS *wp, *wn;
+  IDD_TRY(prepare_train(m, g, pos, neg, &wp, &wn));
+  IDD_CHECK(step_index >= 1 || !apply_update, IDDGCN_EINVAL, "Adam step_index starts at 1");
+  return train_step_body(m, g, pos, neg, wp, wn, lr, beta1, beta2, eps, step_index, false, apply_update, loss_out,
+                         y_out, (cudaStream_t)stream);
+}
+
+// num_steps training steps with the step captured ONCE into a CUDA graph and replayed (the shipped config is
+// launch-bound: ~110 small kernels per step).  first_step_index = Adam t of the first step (>=1).
+// loss_history: DEVICE float[num_steps] or NULL.  Synchronous w.r.t. `stream` ordering: work is enqueued on
+// `stream` (or an internal stream when stream is the legacy default stream, which cannot be captured).
+int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* pos,
+                            const iddgcn_plan_t* neg, float lr, float beta1, float beta2, float eps,
+                            int64_t first_step_index, int64_t num_steps, float* loss_history, void* stream) {
+  TripleWS *wp, *wn;
+  IDD_TRY(prepare_train(m, g, pos, neg, &wp, &wn));
+  IDD_CHECK(first_step_index >= 1 && num_steps >= 0, IDDGCN_EINVAL, "bad step range");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool own = false;
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+    if (!m->own_stream) IDD_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    IDD_CUDA(cudaDeviceSynchronize());
+    st = m->own_stream;
+    own = true;
+  }
+  const int64_t t0 = first_step_index - 1;  // the graph increments the counter before Adam reads it
+  IDD_CUDA(cudaMemcpyAsync(m->step_dev, &t0, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  const bool same = m->graph_exec && m->graph_key[0] == g && m->graph_key[1] == pos && m->graph_key[2] == neg &&
+                    m->graph_hyper[0] == lr && m->graph_hyper[1] == beta1 && m->graph_hyper[2] == beta2 &&
+                    m->graph_hyper[3] == eps;
+  if (!same) {
+    if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    IDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = train_step_body(m, g, pos, neg, wp, wn, lr, beta1, beta2, eps, 0, true, 1, nullptr, nullptr, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != IDDGCN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    IDD_CUDA(ce);
+    ce = cudaGraphInstantiate(&m->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    IDD_CUDA(ce);
+    m->graph_key[0] = g; m->graph_key[1] = pos; m->graph_key[2] = neg;
+    m->graph_hyper[0] = lr; m->graph_hyper[1] = beta1; m->graph_hyper[2] = beta2; m->graph_hyper[3] = eps;
+  }
+  for (int64_t i = 0; i < num_steps; ++i) {
+    IDD_CUDA(cudaGraphLaunch(m->graph_exec, st));
+    if (loss_history)
+      IDD_CUDA(cudaMemcpyAsync(loss_history + i, m->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  if (own) IDD_CUDA(cudaStreamSynchronize(st));
+  return IDDGCN_OK;
+}
+
+int iddgcn_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int64_t step_index, void* stream) {
+  IDD_CHECK(theta && grad && m && v, IDDGCN_EINVAL, "NULL buffer");
+  IDD_CHECK(step_index >= 1, IDDGCN_EINVAL, "Adam step_index starts at 1");
+  return adam_apply(theta, grad, m, v, n, lr, beta1, beta2, eps, step_index, nullptr, (cudaStream_t)stream);
+}
+
+// ---- layer-level entry points (used by the Python IDDGCN_Layer / DistMult autograd functions) ------------
+int iddgcn_relation_transform(const float* S, const float* W, int R, int64_t N, int64_t D, float* Z, void* stream) {
+  IDD_CHECK(S && W && Z, IDDGCN_EINVAL, "NULL buffer");
+  return gemm_f32(false, false, N, D, D, S, D, N * D, W, D, D * D, Z, D, N * D, R, false, (cudaStream_t)stream);
+}
+
+int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb, const float* Hin, const float* Tin, const float* Z,
+                     const float* W_self, const float* W_alpha, const float* b_alpha, int64_t D, float* Hout,
+                     float* Tout, float* alpha_out, void* stream) {
+  IDD_CHECK(p && Z && W_self && W_alpha && b_alpha && Hout && Tout, IDDGCN_EINVAL, "NULL buffer");
+  IDD_CHECK((Hin && Tin) || emb, IDDGCN_EINVAL, "give Hin/Tin or the embedding table");
+  IDD_CHECK(Tout == Hout + (size_t)p->T * D, IDDGCN_EINVAL,
+            "Hout/Tout must be the two planes of one (2,T,D) buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = p->T;
+  if (T == 0) return IDDGCN_OK;
+  const float* hin = Hin;
+  DevBuf<float> tmp;
+  if (!(Hin && Tin)) {
+    IDD_CUDA(tmp.ensure((size_t)2 * T * D));
+    IDD_TRY(gather_embeddings(p, emb, D, tmp.p, st));
+    hin = tmp.p;
+    IDD_TRY(gemm_f32(false, false, 2 * T, D, D, tmp.p, D, 0, W_self, D, 0, Hout, D, 0, 1, false, st));
+  } else if (Tin == Hin + (size_t)T * D) {
+    IDD_TRY(gemm_f32(false, false, 2 * T, D, D, Hin, D, 0, W_self, D, 0, Hout, D, 0, 1, false, st));
+  } else {
+    IDD_TRY(gemm_f32(false, false, T, D, D, Hin, D, 0, W_self, D, 0, Hout, D, 0, 1, false, st));
+    IDD_TRY(gemm_f32(false, false, T, D, D, Tin, D, 0, W_self, D, 0, Tout, D, 0, 1, false, st));
+  }
+  IDD_TRY(layer_combine(p, hin, Z, W_alpha, b_alpha, D, Hout, alpha_out, st));
+  if (tmp.p) IDD_CUDA(cudaStreamSynchronize(st));  // tmp is freed on return
+  return IDDGCN_OK;
+}
+
+// Backward of iddgcn_layer_fwd (SURVEY App. A eq. 5-10).  HT_in / HT_out / dHT_out / dHT_in are (2,T,D) buffers
+// (head plane then tail plane); dHT_out is overwritten with the pre-activation gradients.  Weight gradients are
+// ACCUMULATED into dW_self [D,D], dW_alpha [D,R], db_alpha [R]; dZ [R,N,D] is accumulated when accumulate_dZ != 0,
+// else overwritten.
+int iddgcn_layer_bwd(const iddgcn_plan_t* p, const float* HT_in, const float* HT_out, const float* alpha,
+                     const float* Z, const float* W_self, const float* W_alpha, int64_t D, float* dHT_out,
+                     float* dHT_in, float* dZ, int accumulate_dZ, float* dW_self, float* dW_alpha, float* db_alpha,
+                     void* stream) {
+  IDD_CHECK(p && HT_in && HT_out && alpha && Z && W_self && W_alpha && dHT_out && dHT_in && dZ && dW_self &&
+                dW_alpha && db_alpha, IDDGCN_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = p->T;
+  const int R = p->R;
+  DevBuf<float> dz, gws, sws;
+  IDD_CUDA(dz.ensure((size_t)(T ? T : 1) * R));
+  size_t gw = gemm_tn_workspace_elems(D, D, 2 * T, 1), g2 = gemm_tn_workspace_elems(D, R, T, 1);
+  IDD_CUDA(gws.ensure(gw > g2 ? gw : g2));
+  IDD_CUDA(sws.ensure(colsum_scratch_elems(T, R)));
+  IDD_TRY(layer_bwd_pre(p, HT_out, alpha, Z, D, dHT_out, dz.p, st));
+  IDD_TRY(gemm_tn_splitk_f32(D, D, 2 * T, HT_in, D, 0, dHT_out, D, 0, dW_self, D, 0, 1, true, gws.p, st));
+  IDD_TRY(gemm_tn_splitk_f32(D, R, T, HT_in, D, 0, dz.p, R, 0, dW_alpha, R, 0, 1, true, gws.p, st));
+  IDD_TRY(colsum(dz.p, T, R, db_alpha, 1, sws.p, st));
+  IDD_TRY(segment_scatter(p, dHT_out, alpha, D, dZ, accumulate_dZ, st));
+  IDD_TRY(gemm_f32(false, true, 2 * T, D, D, dHT_out, D, 0, W_self, D, 0, dHT_in, D, 0, 1, false, st));
+  IDD_TRY(layer_bwd_post(dz.p, W_alpha, T, D, R, dHT_in, st));
+  IDD_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
+  return IDDGCN_OK;
+}
+
+// out[plane][n][:] (+)= segment sums of dHT (2,T,D) by head and by tail; alpha NULL -> one plane, weight 1
+int iddgcn_segment_scatter(const iddgcn_plan_t* p, const float* dHT, const float* alpha, int64_t D, float* out,
+                           int accumulate, void* stream) {
+  IDD_CHECK(p && dHT && out, IDDGCN_EINVAL, "NULL buffer");
+  return segment_scatter(p, dHT, alpha, D, out, accumulate, (cudaStream_t)stream);
+}
+
+int iddgcn_distmult_fwd(const iddgcn_plan_t* p, const float* HT, const float* rel_emb, int64_t D, float* y,
+                        void* stream) {
+  IDD_CHECK(p && HT && rel_emb && y, IDDGCN_EINVAL, "NULL buffer");
+  return distmult_fwd(p, HT, rel_emb, D, y, (cudaStream_t)stream);
+}
+
+// dHT (2,T,D) written; d_rel_emb [R,D] ACCUMULATED
+int iddgcn_distmult_bwd(const iddgcn_plan_t* p, const float* HT, const float* rel_emb, const float* y,
+                        const float* dy, int64_t D, float* dHT, float* d_rel_emb, void* stream) {
+  IDD_CHECK(p && HT && rel_emb && y && dy && dHT && d_rel_emb, IDDGCN_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<float> scratch;
+  IDD_CUDA(scratch.ensure(distmult_scratch_elems(p, D)));
+  IDD_TRY(distmult_bwd(p, HT, rel_emb, y, dy, D, dHT, d_rel_emb, scratch.p, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  return IDDGCN_OK;
+}
+
+// dW[r] += S[r]ᵀ·dZ[r]  and  dS[r] (+)= dZ[r]·W[r]ᵀ  — backward of iddgcn_relation_transform
+int iddgcn_relation_transform_bwd(const float* S, const float* W, const float* dZ, int R, int64_t N, int64_t D,
+                                  float* dW, float* dS, int accumulate_dS, void* stream) {
+  IDD_CHECK(S && W && dZ && dW && dS, IDDGCN_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<float> gws;
+  IDD_CUDA(gws.ensure(gemm_tn_workspace_elems(D, D, N, R)));
+  IDD_TRY(gemm_tn_splitk_f32(D, D, N, S, D, N * D, dZ, D, N * D, dW, D, D * D, R, true, gws.p, st));
+  IDD_TRY(gemm_f32(false, true, N, D, D, dZ, D, N * D, W, D, D * D, dS, D, N * D, R, accumulate_dS != 0, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  return IDDGCN_OK;
+}
+
+// Keras BinaryCrossentropy over y = [T_pos positives | rest negatives]; loss_out, dy on device
+int iddgcn_bce_loss_grad(const float* y, int64_t T_pos, int64_t T_total, float grad_scale, float* dy,
+                         float* loss_out, void* stream) {
+  IDD_CHECK(y && dy && loss_out, IDDGCN_EINVAL, "NULL buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<float> scratch;
+  IDD_CUDA(scratch.ensure(bce_scratch_elems(T_total)));
+  IDD_TRY(bce_loss_grad(y, T_pos, T_total, grad_scale, dy, loss_out, scratch.p, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  return IDDGCN_OK;
+}
+
+}  // extern "C"

@@ -278,6 +278,19 @@ int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const fl
   return launch_gather<true>(a, mode, st);
 }
 
+int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64_t D, const float* vals, int mode,
+                   float* dvals, cudaStream_t st) {
+  if (g->nnz == 0) return IDDGCN_OK;
+  const int nvec = (int)(D / 4);
+  if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+  if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+  if (nvec <= 32) return launch_sddmm_mode<32, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+  if (nvec <= 64) return launch_sddmm_mode<32, 2, 4>(g, dS, X, vals, mode, dvals, nvec, st);
+  if (nvec <= 128) return launch_sddmm_mode<32, 4, 2>(g, dS, X, vals, mode, dvals, nvec, st);
+  set_error("feature width D=%lld > 512 is not supported", (long long)D);
+  return IDDGCN_ELIMIT;
+}
+
 }  // namespace iddgcn
 
 using namespace iddgcn;
@@ -305,16 +318,7 @@ int iddgcn_spmm_bwd_vals(const iddgcn_graph_t* g, const float* dS, const float* 
   IDD_TRY(check_common(g, D, vals, vals_mode));
   IDD_CHECK(dS && X && dvals, IDDGCN_EINVAL, "dS, X or dvals is NULL");
   IDD_CHECK(aligned16(dS) && aligned16(X), IDDGCN_EINVAL, "dS and X must be 16-byte aligned");
-  if (g->nnz == 0) return IDDGCN_OK;
-  const int nvec = (int)(D / 4);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
-  if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
-  if (nvec <= 32) return launch_sddmm_mode<32, 1, 8>(g, dS, X, vals, vals_mode, dvals, nvec, st);
-  if (nvec <= 64) return launch_sddmm_mode<32, 2, 4>(g, dS, X, vals, vals_mode, dvals, nvec, st);
-  if (nvec <= 128) return launch_sddmm_mode<32, 4, 2>(g, dS, X, vals, vals_mode, dvals, nvec, st);
-  set_error("feature width D=%lld > 512 is not supported", (long long)D);
-  return IDDGCN_ELIMIT;
+  return sddmm_dispatch(g, dS, X, D, vals, vals_mode, dvals, (cudaStream_t)stream);
 }
 
 int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_mode, float* out_per_rel,

@@ -1,0 +1,587 @@
+// triple.cu — per-triple stage of IDDGCN_Layer.call (prediction/IDDGCN.py:60-79), DistMult (:103-109),
+// the BCE loss of train_step (:161-168) and Keras Adam (:174), forward and backward.
+//
+// Layout: every per-triple activation is a (2, T, D) buffer — plane 0 = head side, plane 1 = tail side —
+// so the two self-kernel matmuls of a layer are ONE GEMM with M = 2T.  One warp owns one triple; each lane
+// keeps NV float4 slices of the D-wide row (D <= 128*NV).  Gather backward passes are segment sums over
+// the plan's by-head / by-tail orderings: no atomics, fixed summation order.
+#include "triple.cuh"
+
+namespace iddgcn {
+
+constexpr int TW = 8;  // warps per block
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 c) {
+  return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w));
+}
+__device__ __forceinline__ float4 f4_sigmoid(float4 a) {
+  return make_float4(sigmoidf_(a.x), sigmoidf_(a.y), sigmoidf_(a.z), sigmoidf_(a.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_emb_kernel(const int32_t* __restrict__ head,
+                                                         const int32_t* __restrict__ tail,
+                                                         const float4* __restrict__ emb, int64_t T, int nvec,
+                                                         float4* __restrict__ HT) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = 2 * T * nvec;
+  if (i >= total) return;
+  const int v = (int)(i % nvec);
+  const int64_t row = i / nvec;  // [0, 2T)
+  const int32_t n = row < T ? head[row] : tail[row - T];
+  HT[i] = __ldg(emb + (int64_t)n * nvec + v);
+}
+
+int gather_embeddings(const iddgcn_plan* p, const float* emb, int64_t D, float* HT, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  const int nvec = (int)(D / 4);
+  const int64_t total = 2 * p->T * nvec;
+  gather_emb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      p->head, p->tail, reinterpret_cast<const float4*>(emb), p->T, nvec, reinterpret_cast<float4*>(HT));
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward epilogue: gate + gathers of Z_i[head], Z_i[tail] + sigmoid
+template <int NV>
+__global__ void __launch_bounds__(TW * 32)
+    layer_combine_kernel(const int32_t* __restrict__ head, const int32_t* __restrict__ tail,
+                         const float4* __restrict__ Hin, const float4* __restrict__ Z,
+                         const float* __restrict__ W_alpha, const float* __restrict__ b_alpha, int64_t T, int64_t N,
+                         int nvec, int R, float4* __restrict__ P, float* __restrict__ alpha_out) {
+  extern __shared__ float s_wa[];  // W_alpha [D][R]
+  const int D = nvec * 4;
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) s_wa[i] = W_alpha[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
+  if (k >= T) return;
+  // logits z_i = Hin[k]·W_alpha[:, i] + b_i
+  float z[RMAX];
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i) z[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + c * 32;
+    if (v < nvec) {
+      const float4 h = __ldg(Hin + k * nvec + v);
+      const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* w = s_wa + (v * 4 + q) * R;
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i)
+          if (i < R) z[i] = fmaf(hv[q], w[i], z[i]);
+      }
+    }
+  }
+  float zmax = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i)
+    if (i < R) {
+      z[i] = warp_sum(z[i]) + b_alpha[i];
+      zmax = fmaxf(zmax, z[i]);
+    }
+  float den = 0.f;
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i)
+    if (i < R) {
+      z[i] = expf(z[i] - zmax);
+      den += z[i];
+    }
+  float gate[RMAX];
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i)
+    if (i < R) {
+      const float a = z[i] / den;  // softmax (IDDGCN.py:66)
+      if (alpha_out && lane == 0) alpha_out[k * R + i] = a;
+      gate[i] = sigmoidf_(a);      // relation_weight (IDDGCN.py:75)
+    }
+  const int32_t nh = head[k], nt = tail[k];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int64_t node = half == 0 ? nh : nt;
+    float4* prow = P + ((int64_t)half * T + k) * nvec;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int v = lane + c * 32;
+      if (v < nvec) {
+        float4 acc = prow[v];
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i)
+          if (i < R) acc = f4_fma(gate[i], __ldg(Z + ((int64_t)i * N + node) * nvec + v), acc);
+        prow[v] = f4_sigmoid(acc);
+      }
+    }
+  }
+}
+
+int layer_combine(const iddgcn_plan* p, const float* Hin, const float* Z, const float* W_alpha, const float* b_alpha,
+                  int64_t D, float* P_inout, float* alpha_out, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  IDD_CHECK(p->R <= RMAX, IDDGCN_ELIMIT, "triple stage supports at most %d relations (got %d)", RMAX, p->R);
+  IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "triple stage needs D %% 4 == 0 and D <= 512 (got %lld)",
+            (long long)D);
+  const int nvec = (int)(D / 4);
+  const unsigned grid = (unsigned)((p->T + TW - 1) / TW);
+  const size_t smem = (size_t)D * p->R * sizeof(float);
+#define IDD_ARGS p->head, p->tail, reinterpret_cast<const float4*>(Hin), reinterpret_cast<const float4*>(Z), W_alpha, \
+                 b_alpha, p->T, p->N, nvec, p->R, reinterpret_cast<float4*>(P_inout), alpha_out
+  if (nvec <= 32) layer_combine_kernel<1><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else if (nvec <= 64) layer_combine_kernel<2><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else layer_combine_kernel<4><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+#undef IDD_ARGS
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward, part 1: through the sigmoid, the gate and the softmax (SURVEY App. A eq. 5-7)
+template <int NV>
+__global__ void __launch_bounds__(TW * 32)
+    layer_bwd_pre_kernel(const int32_t* __restrict__ head, const int32_t* __restrict__ tail,
+                         const float4* __restrict__ HT_out, const float* __restrict__ alpha,
+                         const float4* __restrict__ Z, int64_t T, int64_t N, int nvec, int R,
+                         float4* __restrict__ dHT, float* __restrict__ dz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
+  if (k >= T) return;
+  float dgate[RMAX];
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i) dgate[i] = 0.f;
+  const int32_t nh = head[k], nt = tail[k];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int64_t node = half == 0 ? nh : nt;
+    const int64_t off = ((int64_t)half * T + k) * nvec;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int v = lane + c * 32;
+      if (v < nvec) {
+        const float4 o = __ldg(HT_out + off + v);
+        const float4 g = dHT[off + v];
+        const float4 dp = make_float4(g.x * o.x * (1.f - o.x), g.y * o.y * (1.f - o.y), g.z * o.z * (1.f - o.z),
+                                      g.w * o.w * (1.f - o.w));  // eq. 5
+        dHT[off + v] = dp;
+#pragma unroll
+        for (int i = 0; i < RMAX; ++i)
+          if (i < R) dgate[i] += f4_dot(dp, __ldg(Z + ((int64_t)i * N + node) * nvec + v));  // eq. 6
+      }
+    }
+  }
+  float dal[RMAX], al[RMAX];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RMAX; ++i)
+    if (i < R) {
+      const float dg = warp_sum(dgate[i]);
+      al[i] = alpha[k * R + i];
+      const float gt = sigmoidf_(al[i]);
+      dal[i] = dg * gt * (1.f - gt);
+      s += dal[i] * al[i];
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i)
+      if (i < R) dz[k * R + i] = al[i] * (dal[i] - s);  // eq. 7
+  }
+}
+
+int layer_bwd_pre(const iddgcn_plan* p, const float* HT_out, const float* alpha, const float* Z, int64_t D,
+                  float* dHT_inout, float* dz, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  IDD_CHECK(p->R <= RMAX && D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported R=%d / D=%lld", p->R, (long long)D);
+  const int nvec = (int)(D / 4);
+  const unsigned grid = (unsigned)((p->T + TW - 1) / TW);
+#define IDD_ARGS p->head, p->tail, reinterpret_cast<const float4*>(HT_out), alpha, reinterpret_cast<const float4*>(Z), \
+                 p->T, p->N, nvec, p->R, reinterpret_cast<float4*>(dHT_inout), dz
+  if (nvec <= 32) layer_bwd_pre_kernel<1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else if (nvec <= 64) layer_bwd_pre_kernel<2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else layer_bwd_pre_kernel<4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+#undef IDD_ARGS
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// backward, part 2: dHin += dz · W_alphaᵀ (second term of eq. 9)
+__global__ void __launch_bounds__(256) layer_bwd_post_kernel(const float* __restrict__ dz,
+                                                             const float* __restrict__ W_alpha, int64_t T, int D,
+                                                             int R, float* __restrict__ dHin) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * D) return;
+  const int64_t k = i / D;
+  const int d = (int)(i % D);
+  float acc = dHin[i];
+  for (int r = 0; r < R; ++r) acc = fmaf(dz[k * R + r], __ldg(W_alpha + d * R + r), acc);
+  dHin[i] = acc;
+}
+
+int layer_bwd_post(const float* dz, const float* W_alpha, int64_t T, int64_t D, int R, float* dHin, cudaStream_t st) {
+  if (T == 0) return IDDGCN_OK;
+  layer_bwd_post_kernel<<<(unsigned)((T * D + 255) / 256), 256, 0, st>>>(dz, W_alpha, T, (int)D, R, dHin);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// segment sums over the plan's by-head / by-tail orderings (gather backward without atomics)
+template <int NV, bool GATED>
+__global__ void __launch_bounds__(TW * 32)
+    segment_scatter_kernel(const int32_t* __restrict__ ptr_h, const int32_t* __restrict__ perm_h,
+                           const int32_t* __restrict__ ptr_t, const int32_t* __restrict__ perm_t,
+                           const float4* __restrict__ dP, const float* __restrict__ alpha, int64_t T, int64_t N,
+                           int nvec, int R, float4* __restrict__ out, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
+  if (n >= N) return;
+  constexpr int RC = GATED ? 4 : 1;  // relations accumulated per sweep over the node's triples
+  const int planes = GATED ? R : 1;
+  for (int r0 = 0; r0 < planes; r0 += RC) {
+    float4 acc[RC][NV];
+#pragma unroll
+    for (int i = 0; i < RC; ++i)
+#pragma unroll
+      for (int c = 0; c < NV; ++c) acc[i][c] = f4_zero();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int32_t* ptr = half == 0 ? ptr_h : ptr_t;
+      const int32_t* perm = half == 0 ? perm_h : perm_t;
+      const int beg = ptr[n], end = ptr[n + 1];
+      for (int j = beg; j < end; ++j) {
+        const int64_t k = perm[j];
+        float w[RC];
+#pragma unroll
+        for (int i = 0; i < RC; ++i) {
+          if (GATED) w[i] = (r0 + i < R) ? sigmoidf_(__ldg(alpha + k * R + r0 + i)) : 0.f;
+          else w[i] = 1.f;
+        }
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+          const int v = lane + c * 32;
+          if (v < nvec) {
+            const float4 g = __ldg(dP + ((int64_t)half * T + k) * nvec + v);
+#pragma unroll
+            for (int i = 0; i < RC; ++i) acc[i][c] = f4_fma(w[i], g, acc[i][c]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RC; ++i) {
+      if (r0 + i >= planes) continue;
+      float4* orow = out + ((int64_t)(r0 + i) * N + n) * nvec;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const int v = lane + c * 32;
+        if (v < nvec) {
+          float4 r = acc[i][c];
+          if (accumulate) {
+            const float4 pv = orow[v];
+            r.x += pv.x; r.y += pv.y; r.z += pv.z; r.w += pv.w;
+          }
+          orow[v] = r;
+        }
+      }
+    }
+  }
+}
+
+int segment_scatter(const iddgcn_plan* p, const float* dP, const float* alpha, int64_t D, float* out, int accumulate,
+                    cudaStream_t st) {
+  IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
+  const int nvec = (int)(D / 4);
+  const unsigned grid = (unsigned)((p->N + TW - 1) / TW);
+#define IDD_ARGS p->by_head_ptr, p->by_head_perm, p->by_tail_ptr, p->by_tail_perm, reinterpret_cast<const float4*>(dP), \
+                 alpha, p->T, p->N, nvec, p->R, reinterpret_cast<float4*>(out), accumulate
+  if (alpha) {
+    if (nvec <= 32) segment_scatter_kernel<1, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else if (nvec <= 64) segment_scatter_kernel<2, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else segment_scatter_kernel<4, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  } else {
+    if (nvec <= 32) segment_scatter_kernel<1, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else if (nvec <= 64) segment_scatter_kernel<2, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else segment_scatter_kernel<4, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  }
+#undef IDD_ARGS
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums (db_alpha), two fixed-order stages
+constexpr int CS_BLOCK = 256;
+constexpr int CS_ROWS_PER_BLOCK = 4096;
+
+__global__ void __launch_bounds__(CS_BLOCK) colsum_partial_kernel(const float* __restrict__ in, int64_t rows, int cols,
+                                                                  float* __restrict__ partial) {
+  __shared__ float s[CS_BLOCK];
+  const int64_t r0 = (int64_t)blockIdx.x * CS_ROWS_PER_BLOCK;
+  const int64_t r1 = (r0 + CS_ROWS_PER_BLOCK < rows) ? r0 + CS_ROWS_PER_BLOCK : rows;
+  for (int c = 0; c < cols; ++c) {
+    float acc = 0.f;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += CS_BLOCK) acc += in[r * cols + c];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = CS_BLOCK / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * cols + c] = s[0];
+    __syncthreads();
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t nblocks, int cols,
+                                    float* __restrict__ out, int accumulate) {
+  const int c = threadIdx.x;
+  if (c >= cols) return;
+  float acc = 0.f;
+  for (int64_t b = 0; b < nblocks; ++b) acc += partial[b * cols + c];
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+size_t colsum_scratch_elems(int64_t rows, int cols) {
+  return (size_t)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK + 1) * cols;
+}
+
+int colsum(const float* in, int64_t rows, int cols, float* out, int accumulate, float* scratch, cudaStream_t st) {
+  IDD_CHECK(cols <= 32, IDDGCN_ELIMIT, "colsum supports at most 32 columns");
+  const int64_t nb = (rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK;
+  if (nb > 0) {
+    colsum_partial_kernel<<<(unsigned)nb, CS_BLOCK, 0, st>>>(in, rows, cols, scratch);
+    IDD_LAUNCH_CHECK();
+  }
+  colsum_final_kernel<<<1, 32, 0, st>>>(scratch, nb, cols, out, accumulate);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DistMult decoder
+template <int NV>
+__global__ void __launch_bounds__(TW * 32)
+    distmult_fwd_kernel(const int32_t* __restrict__ rel, const float4* __restrict__ HT,
+                        const float4* __restrict__ rel_emb, int64_t T, int nvec, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
+  if (k >= T) return;
+  const int r = rel[k];
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + c * 32;
+    if (v < nvec) {
+      const float4 h = __ldg(HT + k * nvec + v), t = __ldg(HT + (T + k) * nvec + v);
+      const float4 e = __ldg(rel_emb + (int64_t)r * nvec + v);
+      acc += h.x * e.x * t.x + h.y * e.y * t.y + h.z * e.z * t.z + h.w * e.w * t.w;  // IDDGCN.py:108
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) y[k] = sigmoidf_(acc);
+}
+
+int distmult_fwd(const iddgcn_plan* p, const float* HT, const float* rel_emb, int64_t D, float* y, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
+  const int nvec = (int)(D / 4);
+  const unsigned grid = (unsigned)((p->T + TW - 1) / TW);
+#define IDD_ARGS p->rel, reinterpret_cast<const float4*>(HT), reinterpret_cast<const float4*>(rel_emb), p->T, nvec, y
+  if (nvec <= 32) distmult_fwd_kernel<1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else if (nvec <= 64) distmult_fwd_kernel<2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else distmult_fwd_kernel<4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+#undef IDD_ARGS
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(TW * 32)
+    distmult_bwd_kernel(const int32_t* __restrict__ rel, const float4* __restrict__ HT,
+                        const float4* __restrict__ rel_emb, const float* __restrict__ y,
+                        const float* __restrict__ dy, int64_t T, int nvec, float4* __restrict__ dHT) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
+  if (k >= T) return;
+  const int r = rel[k];
+  const float yk = y[k];
+  const float dq = dy[k] * yk * (1.f - yk);  // eq. 14
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + c * 32;
+    if (v < nvec) {
+      const float4 h = __ldg(HT + k * nvec + v), t = __ldg(HT + (T + k) * nvec + v);
+      const float4 e = __ldg(rel_emb + (int64_t)r * nvec + v);
+      dHT[k * nvec + v] = make_float4(dq * e.x * t.x, dq * e.y * t.y, dq * e.z * t.z, dq * e.w * t.w);
+      dHT[(T + k) * nvec + v] = make_float4(dq * e.x * h.x, dq * e.y * h.y, dq * e.z * h.z, dq * e.w * h.w);
+    }
+  }
+}
+
+// d_rel_emb partials: block (chunk c, relation r) sums its slice of the by-rel run, thread per feature
+constexpr int DR_CHUNK = 2048;
+__global__ void __launch_bounds__(128)
+    distmult_drel_kernel(const int32_t* __restrict__ ptr_r, const int32_t* __restrict__ perm_r,
+                         const float* __restrict__ HT, const float* __restrict__ y, const float* __restrict__ dy,
+                         int64_t T, int D, int nchunk, float* __restrict__ partial /* [R][nchunk][D] */) {
+  const int r = blockIdx.y, c = blockIdx.x;
+  const int beg = ptr_r[r], end = ptr_r[r + 1];
+  const int len = end - beg;
+  const int per = (len + nchunk - 1) / nchunk;
+  const int j0 = beg + c * per;
+  const int j1 = (j0 + per < end) ? j0 + per : end;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int j = j0; j < j1; ++j) {
+      const int64_t k = perm_r[j];
+      const float yk = y[k];
+      const float dq = dy[k] * yk * (1.f - yk);
+      acc = fmaf(dq, HT[k * D + d] * HT[(T + k) * D + d], acc);
+    }
+    partial[((int64_t)r * nchunk + c) * D + d] = acc;
+  }
+}
+
+__global__ void drel_final_kernel(const float* __restrict__ partial, int nchunk, int D, float* __restrict__ out) {
+  const int r = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float acc = 0.f;
+  for (int c = 0; c < nchunk; ++c) acc += partial[((int64_t)r * nchunk + c) * D + d];
+  out[(int64_t)r * D + d] += acc;
+}
+
+static int drel_chunks(int64_t T) {
+  int64_t n = (T + DR_CHUNK - 1) / DR_CHUNK;
+  if (n < 1) n = 1;
+  if (n > 1024) n = 1024;
+  return (int)n;
+}
+
+size_t distmult_scratch_elems(const iddgcn_plan* p, int64_t D) { return (size_t)p->R * drel_chunks(p->T) * D; }
+
+int distmult_bwd(const iddgcn_plan* p, const float* HT, const float* rel_emb, const float* y, const float* dy,
+                 int64_t D, float* dHT, float* d_rel_emb, float* scratch, cudaStream_t st) {
+  if (p->T == 0) return IDDGCN_OK;
+  IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
+  const int nvec = (int)(D / 4);
+  const unsigned grid = (unsigned)((p->T + TW - 1) / TW);
+#define IDD_ARGS p->rel, reinterpret_cast<const float4*>(HT), reinterpret_cast<const float4*>(rel_emb), y, dy, p->T, \
+                 nvec, reinterpret_cast<float4*>(dHT)
+  if (nvec <= 32) distmult_bwd_kernel<1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else if (nvec <= 64) distmult_bwd_kernel<2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+  else distmult_bwd_kernel<4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+#undef IDD_ARGS
+  IDD_LAUNCH_CHECK();
+  if (d_rel_emb) {
+    const int nchunk = drel_chunks(p->T);
+    distmult_drel_kernel<<<dim3(nchunk, p->R), 128, 0, st>>>(p->by_rel_ptr, p->by_rel_perm, HT, y, dy, p->T, (int)D,
+                                                             nchunk, scratch);
+    IDD_LAUNCH_CHECK();
+    drel_final_kernel<<<dim3((unsigned)((D + 127) / 128), p->R), 128, 0, st>>>(scratch, nchunk, (int)D, d_rel_emb);
+    IDD_LAUNCH_CHECK();
+  }
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras BinaryCrossentropy (from_logits=False): clip to [eps, 1-eps], log(p + eps)  
+constexpr int BCE_BLOCK = 256;
+constexpr int BCE_PER_BLOCK = 4096;
+__global__ void __launch_bounds__(BCE_BLOCK)
+    bce_kernel(const float* __restrict__ y, int64_t T_pos, int64_t T_total, float grad_scale, float* __restrict__ dy,
+               float* __restrict__ partial) {
+  __shared__ float s[BCE_BLOCK];
+  const float eps = 1e-7f;
+  const int64_t i0 = (int64_t)blockIdx.x * BCE_PER_BLOCK;
+  const int64_t i1 = (i0 + BCE_PER_BLOCK < T_total) ? i0 + BCE_PER_BLOCK : T_total;
+  const float inv_n = 1.0f / (float)T_total;
+  float acc = 0.f;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += BCE_BLOCK) {
+    const float p = y[i];
+    const float pc = fminf(fmaxf(p, eps), 1.0f - eps);
+    const bool inside = (p >= eps) && (p <= 1.0f - eps);
+    float term, g;
+    if (i < T_pos) {  // label 1
+      term = -logf(pc + eps);
+      g = -1.0f / (pc + eps);
+    } else {          // label 0
+      term = -logf(1.0f - pc + eps);
+      g = 1.0f / (1.0f - pc + eps);
+    }
+    acc += term;
+    dy[i] = inside ? g * inv_n * grad_scale : 0.f;  // eq. 15
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = BCE_BLOCK / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+
+__global__ void bce_final_kernel(const float* __restrict__ partial, int64_t nb, int64_t T_total,
+                                 float* __restrict__ loss_out) {
+  if (threadIdx.x != 0) return;
+  float acc = 0.f;
+  for (int64_t b = 0; b < nb; ++b) acc += partial[b];
+  loss_out[0] = acc / (float)T_total;
+}
+
+size_t bce_scratch_elems(int64_t T_total) { return (size_t)((T_total + BCE_PER_BLOCK - 1) / BCE_PER_BLOCK + 1); }
+
+int bce_loss_grad(const float* y, int64_t T_pos, int64_t T_total, float grad_scale, float* dy, float* loss_out,
+                  float* scratch, cudaStream_t st) {
+  IDD_CHECK(T_total > 0, IDDGCN_EINVAL, "BCE over zero predictions");
+  const int64_t nb = (T_total + BCE_PER_BLOCK - 1) / BCE_PER_BLOCK;
+  bce_kernel<<<(unsigned)nb, BCE_BLOCK, 0, st>>>(y, T_pos, T_total, grad_scale, dy, scratch);
+  IDD_LAUNCH_CHECK();
+  bce_final_kernel<<<1, 32, 0, st>>>(scratch, nb, T_total, loss_out);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Keras Adam (OptimizerV2): lr_t = lr·sqrt(1-b2^t)/(1-b1^t); theta -= lr_t·m/(sqrt(v)+eps)   
+__global__ void __launch_bounds__(256)
+    adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, int64_t step,
+                const int64_t* __restrict__ step_dev) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t t = step_dev ? *step_dev : step;
+  // double keeps b^t accurate for t in the thousands; one pow per thread is negligible here
+  const double c1 = 1.0 - pow((double)b1, (double)t), c2 = 1.0 - pow((double)b2, (double)t);
+  const float lr_t = (float)((double)lr * sqrt(c2) / c1);
+  const float g = grad[i];
+  const float mi = b1 * m[i] + (1.0f - b1) * g;
+  const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+int adam_apply(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float b1, float b2,
+               float eps, int64_t step, const int64_t* step_dev, cudaStream_t st) {
+  if (n <= 0) return IDDGCN_OK;
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, eps, step, step_dev);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+__global__ void increment_kernel(int64_t* c) { *c += 1; }
+int increment_counter(int64_t* counter, cudaStream_t st) {
+  increment_kernel<<<1, 1, 0, st>>>(counter);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+}  // namespace iddgcn

@@ -157,39 +157,67 @@ int iddgcn_plan_create(const int64_t* head, const int64_t* rel, const int64_t* t
 int iddgcn_plan_destroy(iddgcn_plan_t* p);
 
 /* ------------------------------------------------------------------------
- * Layer-level operators (IDDGCN_Layer.call, prediction/IDDGCN.py:60-79).
+ * Layer-level operators (IDDGCN_Layer.call, prediction/IDDGCN.py:60-79) and
+ * their backward (what tape.gradient emits for them, IDDGCN.py:172; maths in
+ * SURVEY.md Appendix A).  Per-triple activations are (2,T,D) buffers: plane 0
+ * = head side, plane 1 = tail side.
  *
  * iddgcn_relation_transform: Z[r] = S[r] · W[r]  ([R,N,D]·[R,D,D]) — the
  *   per-relation transform hoisted from the T gathered rows (IDDGCN.py:76-77)
  *   to the N aggregated rows; same dot products, same values.
+ *   _bwd: dW[r] += S[r]ᵀ·dZ[r];  dS[r] (+)= dZ[r]·W[r]ᵀ.
  * iddgcn_layer_fwd: for every triple k
  *     alpha = softmax(Hin[k]·W_alpha + b_alpha); gate_i = sigmoid(alpha_i)   (:66,:75)
  *     P_H = Hin[k]·W_self + Σ_i gate_i · Z_i[head_k]                          (:62,:76)
  *     P_T = Tin[k]·W_self + Σ_i gate_i · Z_i[tail_k]                          (:63,:77)
  *     Hout = sigmoid(P_H), Tout = sigmoid(P_T)                                (:79)
  *   Hin/Tin may be NULL: then they are gathered from `emb` rows head_k / tail_k
- *   (the Embedding lookups, IDDGCN.py:226-227).  alpha_out [T,R] is saved for
- *   the backward pass (may be NULL for inference).
- * iddgcn_layer_bwd: given dHout,dTout produces
- *     dPH,dPT [T,D] (pre-activation grads), dz [T,R] (softmax-logit grads),
- *     dHin,dTin [T,D] (if Hin given; else they are segment-summed into demb),
- *   SURVEY App. A eq. 5-9.
+ *   (the Embedding lookups, IDDGCN.py:226-227).  Hout/Tout must be the two
+ *   planes of one (2,T,D) buffer.  alpha_out [T,R] is saved for the backward
+ *   pass (may be NULL for inference).
+ * iddgcn_layer_bwd: dHT_out holds dL/d(Hout,Tout) on entry and is overwritten
+ *   with the pre-activation gradients; writes dHT_in; ACCUMULATES dW_self,
+ *   dW_alpha, db_alpha; dZ [R,N,D] accumulated or overwritten.
+ * iddgcn_segment_scatter: gradient of a row gather without atomics —
+ *   out[i][n] (+)= Σ_{k:head_k=n} w_i(k)·dHT[0][k] + Σ_{k:tail_k=n} w_i(k)·dHT[1][k],
+ *   w_i(k) = sigmoid(alpha[k][i]) (R planes) or 1 when alpha is NULL (1 plane;
+ *   UnsortedSegmentSum of tf.nn.embedding_lookup, IDDGCN.py:71-72,226-227).
+ * iddgcn_distmult_fwd/_bwd: DistMult.call (IDDGCN.py:103-109):
+ *   y = sigmoid(Σ_d H·Rel[r]·T); bwd writes dHT and ACCUMULATES d_rel_emb.
+ * iddgcn_bce_loss_grad: Keras BinaryCrossentropy (clip 1e-7, log(p+1e-7)) on
+ *   y = [T_pos positives | negatives] (IDDGCN.py:161-166); loss_out[0] = mean,
+ *   dy = d mean/dy · grad_scale (the reference's loss *= 1/N, :168).
  * ------------------------------------------------------------------------ */
 int iddgcn_relation_transform(const float* S, const float* W, int R, int64_t N, int64_t D,
                               float* Z, void* stream);
+int iddgcn_relation_transform_bwd(const float* S, const float* W, const float* dZ, int R, int64_t N, int64_t D,
+                                  float* dW, float* dS, int accumulate_dS, void* stream);
 int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb,
                      const float* Hin, const float* Tin, const float* Z,
                      const float* W_self, const float* W_alpha, const float* b_alpha,
                      int64_t D, float* Hout, float* Tout, float* alpha_out, void* stream);
+int iddgcn_layer_bwd(const iddgcn_plan_t* p, const float* HT_in, const float* HT_out, const float* alpha,
+                     const float* Z, const float* W_self, const float* W_alpha, int64_t D,
+                     float* dHT_out, float* dHT_in, float* dZ, int accumulate_dZ,
+                     float* dW_self, float* dW_alpha, float* db_alpha, void* stream);
+int iddgcn_segment_scatter(const iddgcn_plan_t* p, const float* dHT, const float* alpha, int64_t D,
+                           float* out, int accumulate, void* stream);
+int iddgcn_distmult_fwd(const iddgcn_plan_t* p, const float* HT, const float* rel_emb, int64_t D,
+                        float* y, void* stream);
+int iddgcn_distmult_bwd(const iddgcn_plan_t* p, const float* HT, const float* rel_emb, const float* y,
+                        const float* dy, int64_t D, float* dHT, float* d_rel_emb, void* stream);
+int iddgcn_bce_loss_grad(const float* y, int64_t T_pos, int64_t T_total, float grad_scale,
+                         float* dy, float* loss_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Whole-model handle — get_IDDGCN_Model (IDDGCN.py:201-285): Embedding(N,D),
- * three IDDGCN_Layer all fed the raw embedding table, DistMult decoder
+ * L IDDGCN_Layer all fed the raw embedding table, DistMult decoder
  * (IDDGCN.py:82-109); IDDGCN_Model.train_step (IDDGCN.py:123-178): positive +
  * negative forward, BinaryCrossentropy (clip 1e-7) · 1/N, backward, Keras Adam.
  *
  * Parameters live in ONE flat fp32 device buffer in Keras trainable_weights
- * order (so Adam is a single fused launch and .h5 I/O is a slice table):
+ * order, each tensor padded to a multiple of 4 floats (so Adam is a single
+ * fused launch and .h5 I/O is a slice table, iddgcn_model_param_layout):
  *   entity_embeddings [N,D];
  *   per layer l=0..L-1: relation_kernels [R,D,D], self_kernel [D,D],
  *                       relation_weights [R] (unused by call, IDDGCN.py:39-44),
@@ -199,20 +227,32 @@ int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb,
 int iddgcn_model_create(int64_t num_entities, int num_relations, int64_t dim, int num_layers,
                         iddgcn_model_t** out);
 int iddgcn_model_destroy(iddgcn_model_t* m);
+/* length of the flat buffer (floats, including padding) */
 int64_t iddgcn_model_num_params(const iddgcn_model_t* m);
+/* offsets[2+5L], sizes[2+5L]: start and element count of each weight in Keras order */
+int iddgcn_model_param_layout(const iddgcn_model_t* m, int64_t* offsets, int64_t* sizes);
 /* device pointer to the flat parameter buffer / its gradient / Adam moments */
 int iddgcn_model_buffers(iddgcn_model_t* m, float** params, float** grads, float** adam_m, float** adam_v);
+/* drop activations cached for a plan (call before destroying the plan) */
+int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p);
 /* y [T] = model(head, rel, tail | graph, optional edge vals)   (IDDGCN.py:147-153, IDDGCN_eval.py:97-105) */
 int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p,
                          const float* vals, int vals_mode, float* y, void* stream);
 /* One training step (IDDGCN.py:123-178).  loss_out: DEVICE float[1] receiving the
  * BCE mean BEFORE the 1/N scaling (what tf.print(loss) shows, :167); y_out
- * [T_pos+T_neg] optional.  step_index t>=1 drives Adam bias correction.
- * apply_update=0 leaves parameters untouched (gradients only). */
+ * [T_pos+T_neg] optional (device).  step_index t>=1 drives Adam bias correction.
+ * apply_update=0 leaves parameters untouched (gradients only).  neg may be NULL. */
 int iddgcn_model_train_step(iddgcn_model_t* m, const iddgcn_graph_t* g,
                             const iddgcn_plan_t* pos, const iddgcn_plan_t* neg,
                             float lr, float beta1, float beta2, float eps, int64_t step_index,
                             int apply_update, float* loss_out, float* y_out, void* stream);
+/* num_steps training steps; the step is captured once into a CUDA graph and
+ * replayed (model.fit(epochs=5000) of IDDGCN.py:399-412 is launch-bound on a B200).
+ * loss_history: DEVICE float[num_steps] or NULL. */
+int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g,
+                            const iddgcn_plan_t* pos, const iddgcn_plan_t* neg,
+                            float lr, float beta1, float beta2, float eps,
+                            int64_t first_step_index, int64_t num_steps, float* loss_history, void* stream);
 /* Backward of a scalar objective through model_forward for one plan:
  * dy [T] is ∂L/∂y.  Accumulates parameter grads into the grads buffer
  * (zero_grads!=0 clears it first) and, if dvals!=NULL, writes ∂L/∂vals [nnz]

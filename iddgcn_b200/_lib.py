@@ -60,6 +60,10 @@ _SIGNATURES = {
     "iddgcn_model_train_loop": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                           C.c_int64, vp, vp]),
     "iddgcn_model_backward": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp]),
+    "iddgcn_subgraph_triples": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64, c_i64p, vp]),
+    "iddgcn_block_relation_sums": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp]),
+    "iddgcn_explain_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int64, vp, vp, vp, vp]),
+    "iddgcn_structure_grad": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
     "iddgcn_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                    vp]),
 }

@@ -266,6 +266,35 @@ int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddg
 int iddgcn_adam_step(float* theta, const float* grad, float* m, float* v, int64_t n,
                      float lr, float beta1, float beta2, float eps, int64_t step_index, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Explainer support — explanation/GnnExplainer.py:13-74, IDDGCN_explain.py:16-120.
+ * The reference explains one test triple at a time on its 1-hop computation
+ * graph.  Here B triples are batched block-diagonally: triple b's sub-graph
+ * uses node ids [b·N, (b+1)·N) of one graph with B·N nodes (embeddings tiled),
+ * so one forward/backward of the kernels above serves the whole batch.
+ *
+ * iddgcn_subgraph_triples: emits, for every triple b, all stored edges of the
+ *   full graph g that touch head[b] or tail[b] (get_computation_graph,
+ *   GnnExplainer.py:18-24) as int64 (head+b·N, rel, tail+b·N) rows, duplicates
+ *   included (graph_build removes them).  head/tail: DEVICE int64[B].  Call with
+ *   triples_out = NULL to obtain *M_out, then with a DEVICE buffer of M rows.
+ * iddgcn_block_relation_sums: c[r][b] = Σ a_e over block b of relation r
+ *   (structure_loss counts, IDDGCN_explain.py:31-34), c is [R,B].
+ * iddgcn_explain_loss: loss_b = -before_b·log(pred_b+1e-5) (GnnExplainer.py:48);
+ *   with targets != NULL: (that + mean_i (target_i - c_ib/Σ_i c_ib)²)/2
+ *   (IDDGCN_explain.py:68-73).  Writes loss[B], dy[B] = ∂loss/∂pred and
+ *   coef[R,B] = ∂loss/∂c.
+ * iddgcn_structure_grad: dvals[e] += coef[rel_e][block_e]·∂a_e/∂vals[e].
+ * ------------------------------------------------------------------------ */
+int iddgcn_subgraph_triples(const iddgcn_graph_t* g, const int64_t* head, const int64_t* tail, int64_t B,
+                            int64_t* triples_out, int64_t capacity_rows, int64_t* M_out, void* stream);
+int iddgcn_block_relation_sums(const iddgcn_graph_t* g, const float* vals, int vals_mode, int64_t N, int64_t B,
+                               float* out, void* stream);
+int iddgcn_explain_loss(const float* before, const float* pred, const float* c, const float* targets, int R,
+                        int64_t B, float* loss, float* dy, float* coef, void* stream);
+int iddgcn_structure_grad(const iddgcn_graph_t* g, const float* vals, int vals_mode, const float* coef,
+                          int64_t N, int64_t B, float* dvals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

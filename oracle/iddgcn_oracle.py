@@ -547,3 +547,47 @@ def eval_protocol(p: ModelParams, X_train, X_test_pos, X_test_neg, N=845, R=4, t
     return {"tp": int(tp), "tn": int(tn), "fp": int(fp), "fn": int(fn),
             "acc": (tn + tp) / (tn + fp + fn + tp), "roc_auc": float(roc_auc_score(y_true, preds)),
             "aupr": float(auc(reca, prec)), "preds": preds, "y_true": y_true}
+
+
+def explainer_run(p: ModelParams, adjacency_data, triples, init_value, *, epochs=5, lr=1e-3, threshold=0.2,
+                  structure_target=None, shared_optimizer=True, k=10):
+    """The per-triple mask-optimisation loop of GnnExplainer.replica_step (GnnExplainer.py:26-74; structure_target=None,
+    epochs=5, threshold=0.2) and IDDGCN_explain.wgnnexplainer_step (IDDGCN_explain.py:43-120; structure_target=
+    [0.4,0.4,0.1,0.1], epochs=10, threshold=0.15).
+
+    Reference semantics kept: R dense (N,N) mask variables all initialised to `init_value` (GnnExplainer.py:123-134);
+    gradients reach a mask only at the sub-graph's edge positions (SparseDenseCwiseMul); ONE Keras Adam shared by all
+    triples whose slots and iteration count are never reset while the masks are (GnnExplainer.py:72-73,122) — so with
+    shared_optimizer=True the dense Adam state carries over and every entry with stale momentum keeps moving.
+    shared_optimizer=False is the batched variant: fresh Adam state per triple (identical for the first triple).
+    Returns a list of (top-k triples [k',3] (h,r,t), scores [k'], final loss)."""
+    N = p.emb.shape[0]
+    R = p.rel_emb.shape[0]
+    dt = p.emb.dtype
+    init_value = np.asarray(init_value, dt)
+    adjacency_data = np.asarray(adjacency_data)
+    m = np.zeros((R, N, N), dt); v = np.zeros((R, N, N), dt)
+    t_step = 0
+    out = []
+    for trip in np.asarray(triples):
+        if not shared_optimizer:
+            m[:] = 0; v[:] = 0; t_step = 0
+        masks = np.broadcast_to(init_value, (R, N, N)).copy()           # mask.assign(init_value)
+        comp = get_computation_graph(trip[0], trip[2], adjacency_data)  # GnnExplainer.py:27
+        adj = get_adj_mats(comp, N, R)                                  # :28
+        loss = 0.0
+        for _ in range(epochs):                                         # :30
+            logits = [masks[i][a.indices[:, 1], a.indices[:, 2]] for i, a in enumerate(adj)]
+            loss, dmask, _, _ = explainer_loss_and_grad(p, adj, trip, logits, structure_target=structure_target)
+            g = np.zeros((R, N, N), dt)
+            for i, a in enumerate(adj):
+                np.add.at(g[i], (a.indices[:, 1], a.indices[:, 2]), dmask[i])
+            t_step += 1
+            for i in range(R):                                          # dense Adam on every mask entry (:52)
+                adam_update(masks[i], g[i], m[i], v[i], t_step, lr)
+        scores = []
+        for i, a in enumerate(adj):
+            scores.append(a.values.astype(dt) * sigmoid(masks[i][a.indices[:, 1], a.indices[:, 2]]))   # :56
+        tk, sk = top_k_edges(adj, scores, k=k, threshold=threshold)     # :57-71
+        out.append((tk, sk, loss))
+    return out

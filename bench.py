@@ -315,7 +315,8 @@ def run_ours(args, wl):
         traffic = tj.get(wl["name"], {}).get(dom)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": f"gather_rows_kernel ({'spmm_fwd' if dom == 'fwd' else 'spmm_bwd_x'})",
+    kname = "gather_rows_kernel" if os.environ.get("IDDGCN_SPMM_V1") == "1" else "stream_rows_kernel"
+    roofline = {"bound": "hbm", "kernel": f"{kname} ({'iddgcn_spmm_fwd' if dom == 'fwd' else 'iddgcn_spmm_bwd_x'})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
                 "fwd": {"ms": fwd_ms, "bytes": bf, "GBps": bf / fwd_ms / 1e6, "frac": bf / fwd_ms / 1e6 / peak},

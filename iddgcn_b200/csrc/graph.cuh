@@ -17,7 +17,17 @@ struct iddgcn_graph {
   int32_t* csc_rowptr = nullptr;  // [R*N+1]
   int32_t* csc_row = nullptr;     // [nnz]
   int32_t* csc_perm = nullptr;    // [nnz]
+  // node-major view of the CSC used by the backward kernel: all in-edges of source node k, relations in order,
+  // are one contiguous run, so dX = Σ_r A_rᵀ·dS_r is a plain CSR gather over dS viewed as [(R·n_rows), D]
+  int32_t* bwd_rowptr = nullptr;  // [N+1]
+  int32_t* bwd_src = nullptr;     // [nnz]  r·n_rows + local head
+  int32_t* bwd_perm = nullptr;    // [nnz]  CSR edge id
   float* rel_sums_scratch = nullptr;
+  // lazily created by iddgcn_spmm_fwd_bwd_host and kept for the next call (mutable cache)
+  mutable float* host_ws = nullptr;
+  mutable size_t host_ws_elems = 0;
+  mutable cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
+  mutable cudaEvent_t host_events[3] = {nullptr, nullptr, nullptr};
 };
 
 // Triples of one model call, plus the orderings that make every gather-backward a segment sum.

@@ -98,6 +98,34 @@ __global__ void segment_ptr_kernel(const uint64_t* __restrict__ keys, size_t nnz
   ptr[s] = (int32_t)lo;
 }
 
+// in-degree of node k summed over relations (+ a trailing 0 so the scan yields the total)
+__global__ void bwd_count_kernel(const int32_t* __restrict__ csc_rowptr, size_t N, int R, uint32_t* __restrict__ cnt) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > N) return;
+  uint32_t c = 0;
+  if (k < N)
+    for (int r = 0; r < R; ++r) c += (uint32_t)(csc_rowptr[(size_t)r * N + k + 1] - csc_rowptr[(size_t)r * N + k]);
+  cnt[k] = c;
+}
+
+// thread per (relation r, node k): copy its CSC run to its place in the node-major arrays
+__global__ void bwd_fill_kernel(const int32_t* __restrict__ csc_rowptr, const int32_t* __restrict__ csc_row,
+                                const int32_t* __restrict__ csc_perm, size_t N, int R, int64_t n_rows,
+                                const int32_t* __restrict__ bwd_rowptr, int32_t* __restrict__ bwd_src,
+                                int32_t* __restrict__ bwd_perm) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * (size_t)R) return;
+  const size_t k = i / R;
+  const int r = (int)(i % R);
+  int dst = bwd_rowptr[k];
+  for (int q = 0; q < r; ++q) dst += csc_rowptr[(size_t)q * N + k + 1] - csc_rowptr[(size_t)q * N + k];
+  const int beg = csc_rowptr[(size_t)r * N + k], end = csc_rowptr[(size_t)r * N + k + 1];
+  for (int e = beg; e < end; ++e, ++dst) {
+    bwd_src[dst] = (int32_t)((int64_t)r * n_rows + csc_row[e]);
+    bwd_perm[dst] = csc_perm[e];
+  }
+}
+
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device, int64_t N, int R, int64_t row_lo,
@@ -203,6 +231,25 @@ static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device,
     IDD_CUDA(cudaMemsetAsync(g->csr_rowptr, 0, (csr_segs + 1) * sizeof(int32_t), st));
     IDD_CUDA(cudaMemsetAsync(g->csc_rowptr, 0, (csc_segs + 1) * sizeof(int32_t), st));
   }
+  // node-major backward view
+  {
+    const size_t Nz = (size_t)N;
+    IDD_CUDA(cudaMalloc((void**)&g->bwd_rowptr, (Nz + 1) * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->bwd_src, (nnz ? nnz : 1) * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&g->bwd_perm, (nnz ? nnz : 1) * sizeof(int32_t)));
+    DevBuf<uint32_t> scr2;
+    IDD_CUDA(scr2.ensure(scan_scratch_elems(Nz + 1)));
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(g->bwd_rowptr);
+    bwd_count_kernel<<<blocks_for(Nz + 1, 256), 256, 0, st>>>(g->csc_rowptr, Nz, R, cnt);
+    IDD_LAUNCH_CHECK();
+    IDD_TRY(exclusive_scan_u32(cnt, cnt, Nz + 1, scr2.p, st));
+    if (nnz) {
+      bwd_fill_kernel<<<blocks_for(Nz * (size_t)R, 256), 256, 0, st>>>(g->csc_rowptr, g->csc_row, g->csc_perm, Nz, R,
+                                                                       n_rows, g->bwd_rowptr, g->bwd_src, g->bwd_perm);
+      IDD_LAUNCH_CHECK();
+    }
+    IDD_CUDA(cudaStreamSynchronize(st));  // scr2 is freed at the end of this scope
+  }
   g->nnz = (int64_t)nnz;
   // per-relation counts: R+1 strided reads of the CSR row pointer
   std::vector<int32_t> bounds(R + 1, 0);
@@ -218,7 +265,13 @@ static void graph_free(iddgcn_graph* g) {
   if (!g) return;
   cudaFree(g->csr_rowptr); cudaFree(g->csr_col); cudaFree(g->csr_row);
   cudaFree(g->csc_rowptr); cudaFree(g->csc_row); cudaFree(g->csc_perm);
+  cudaFree(g->bwd_rowptr); cudaFree(g->bwd_src); cudaFree(g->bwd_perm);
   cudaFree(g->rel_sums_scratch);
+  cudaFree(g->host_ws);
+  for (int i = 0; i < 3; ++i) {
+    if (g->host_streams[i]) cudaStreamDestroy(g->host_streams[i]);
+    if (g->host_events[i]) cudaEventDestroy(g->host_events[i]);
+  }
   delete g;
 }
 

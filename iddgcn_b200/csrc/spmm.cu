@@ -11,6 +11,7 @@
 // walks CSC rows (r, tail) with all relations fused into a single dX write, so neither needs
 // atomics and the summation order is fixed (ascending neighbour index, as TF-CPU does).
 // Edge weights (explicit values or sigmoid(mask)) are applied in registers.
+#include <stdlib.h>
 #include "graph.cuh"
 
 namespace iddgcn {
@@ -108,6 +109,110 @@ __global__ void __launch_bounds__(SPMM_THREADS)
       st_stream_f4(orow + vi, r);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2 gather: edge-index tiles staged in shared memory, edges consumed as one flat stream.
+//
+// A slice of LPR lanes owns a CHUNK of LPR consecutive output rows.  Lane l fetches the end pointer of row l (one
+// coalesced load for the whole chunk); the chunk's index range [ptr[r0], ptr[r0+LPR]) is contiguous, so it is staged
+// into a shared-memory slab with coalesced loads (weights too, with the sigmoid applied once per edge).  The slice
+// then walks the edges in batches of U regardless of row boundaries — U independent 128-bit row gathers are always in
+// flight — and flushes the accumulator whenever the stream crosses a row end (a slice-uniform test).  Per chunk there
+// are two dependent index latencies instead of two per row, which is what limited v1 at an average degree of 10.
+//   out[o, :] (+)= sum_{e in ptr[o]..ptr[o+1]} w(e) * src[idx[e], :]
+// forward : ptr=csr_rowptr, idx=csr_col,  src=X,                  weight index e
+// backward: ptr=bwd_rowptr, idx=bwd_src,  src=dS as [(R·n_rows),D], weight index perm[e]
+constexpr int SLAB = 512;  // staged indices per warp
+
+template <int LPR, int U, int MODE, bool USE_PERM>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    stream_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                       const int32_t* __restrict__ perm, const float* __restrict__ vals,
+                       const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
+                       int nvec, int accumulate) {
+  constexpr int SUBS = 32 / LPR;
+  constexpr int SUB_SLAB = SLAB / SUBS;
+  constexpr bool WEIGHTED = MODE != IDDGCN_VALS_ONES;
+  __shared__ int32_t s_idx[SPMM_THREADS / 32][SLAB];
+  __shared__ float s_w[WEIGHTED ? SPMM_THREADS / 32 : 1][WEIGHTED ? SLAB : 1];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * (SPMM_THREADS / 32) + warp) * SUBS + sub;
+  const int64_t r0 = row_begin + chunk * LPR;
+  if (r0 >= row_end) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int nrows = (row_end - r0 < LPR) ? (int)(row_end - r0) : LPR;
+  int32_t* const sl_idx = &s_idx[warp][sub * SUB_SLAB];
+  float* const sl_w = WEIGHTED ? &s_w[warp][sub * SUB_SLAB] : nullptr;
+
+  const int chunk_beg = ld_stream_i32(ptr + r0);
+  const int my_end = (l < nrows) ? ld_stream_i32(ptr + r0 + l + 1) : 0x7fffffff;
+  const int chunk_end = __shfl_sync(mask, my_end, nrows - 1, LPR);
+  const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
+  float4* __restrict__ out4 = reinterpret_cast<float4*>(out) + (size_t)r0 * nvec;
+
+  int row = 0;
+  int cur_end = __shfl_sync(mask, my_end, 0, LPR);
+  int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto flush = [&]() {
+    if (l < nvec) {
+      float4 r = acc;
+      float4* o = out4 + (size_t)row * nvec + l;
+      if (accumulate) {
+        const float4 prev = *o;
+        r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+      }
+      st_stream_f4(o, r);
+    }
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    ++row;
+    cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
+    if (row >= nrows) cur_end = 0x7fffffff;
+  };
+
+  while (pos < chunk_end) {
+    if (pos + U > slab_hi && slab_hi < chunk_end) {  // refill the slab starting at the current position
+      __syncwarp(mask);
+      slab_lo = pos;
+      slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
+      for (int q = l; q < slab_hi - slab_lo; q += LPR) {
+        const int e = slab_lo + q;
+        sl_idx[q] = ld_stream_i32(idx + e);
+        if (WEIGHTED) sl_w[q] = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + e) : e);
+      }
+      __syncwarp(mask);
+    }
+    const int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
+    float4 v[U];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < n) {
+        const int sidx = sl_idx[pos + u - slab_lo];
+        if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
+        v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < n) {
+        while (cur_end == pos + u) flush();
+        if (WEIGHTED) {
+          acc.x = fmaf(w[u], v[u].x, acc.x); acc.y = fmaf(w[u], v[u].y, acc.y);
+          acc.z = fmaf(w[u], v[u].z, acc.z); acc.w = fmaf(w[u], v[u].w, acc.w);
+        } else {
+          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+        }
+      }
+    }
+    pos += n;
+  }
+  while (row < nrows) flush();
 }
 
 // SDDMM: dvals[e] = <dS[seg(e), :], X[col[e], :]> (· σ'(vals[e]) in SIGMOID mode), CSR edge order.
@@ -253,6 +358,46 @@ static int launch_sddmm_mode(const iddgcn_graph* g, const float* dS, const float
   return IDDGCN_OK;
 }
 
+struct StreamArgs {
+  const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
+  int64_t row_begin, row_end; int nvec; int accumulate;
+};
+
+template <int LPR, bool USE_PERM>
+static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
+  const int64_t rows = a.row_end - a.row_begin;
+  if (rows <= 0) return IDDGCN_OK;
+  constexpr int rows_per_block = (SPMM_THREADS / 32) * 32;  // every warp covers 32 rows (SUBS chunks of LPR)
+  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
+#define IDD_STREAM(MODE_)                                                                                     \
+  stream_rows_kernel<LPR, 8, MODE_, USE_PERM><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(                     \
+      a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate)
+  if (mode == IDDGCN_VALS_ONES) IDD_STREAM(IDDGCN_VALS_ONES);
+  else if (mode == IDDGCN_VALS_EXPLICIT) IDD_STREAM(IDDGCN_VALS_EXPLICIT);
+  else IDD_STREAM(IDDGCN_VALS_SIGMOID);
+#undef IDD_STREAM
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+template <bool USE_PERM>
+static int launch_stream(const StreamArgs& a, int mode, cudaStream_t st) {
+  if (a.nvec <= 8) return launch_stream_mode<8, USE_PERM>(a, mode, st);
+  if (a.nvec <= 16) return launch_stream_mode<16, USE_PERM>(a, mode, st);
+  return launch_stream_mode<32, USE_PERM>(a, mode, st);
+}
+
+// IDDGCN_SPMM_V1=1 selects the v1 (row-at-a-time) kernels for A/B measurements; D > 128 always uses v1.
+static bool use_v1() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("IDDGCN_SPMM_V1");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 static int check_common(const iddgcn_graph* g, int64_t D, const float* vals, int mode) {
   IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
   IDD_CHECK(D > 0 && (D % 4) == 0, IDDGCN_EINVAL, "feature width D=%lld must be a positive multiple of 4",
@@ -267,12 +412,20 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
                    int64_t row_begin, int64_t row_end, cudaStream_t st) {
+  if (D <= 128 && !use_v1()) {
+    StreamArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, (int)(D / 4), 0};
+    return launch_stream<false>(a, mode, st);
+  }
   GatherArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, 1, 0, 0, (int)(D / 4), 0};
   return launch_gather<false>(a, mode, st);
 }
 
 int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
                      int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st) {
+  if (D <= 128 && !use_v1()) {
+    StreamArgs a{g->bwd_rowptr, g->bwd_src, g->bwd_perm, vals, dS, dX, row_begin, row_end, (int)(D / 4), accumulate};
+    return launch_stream<true>(a, mode, st);
+  }
   GatherArgs a{g->csc_rowptr, g->csc_row, g->csc_perm, vals, dS, dX, row_begin, row_end, g->R, g->N, g->n_rows,
                (int)(D / 4), accumulate};
   return launch_gather<true>(a, mode, st);
@@ -343,16 +496,22 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
   IDD_TRY(check_common(g, D, nullptr, IDDGCN_VALS_ONES));
   IDD_CHECK(X_host && dS_host, IDDGCN_EINVAL, "X_host or dS_host is NULL");
   const size_t xN = (size_t)g->N * D, sN = (size_t)g->R * g->n_rows * D;
-  DevBuf<float> dX_in, dS_in, dS_out, dX_out;
-  IDD_CUDA(dX_in.ensure(xN)); IDD_CUDA(dS_in.ensure(sN)); IDD_CUDA(dS_out.ensure(sN)); IDD_CUDA(dX_out.ensure(xN));
-  cudaStream_t s_in, s_cmp, s_out;
-  IDD_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  IDD_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
-  IDD_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  cudaEvent_t ev_x, ev_ds, ev_chunk;
-  IDD_CUDA(cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming));
-  IDD_CUDA(cudaEventCreateWithFlags(&ev_ds, cudaEventDisableTiming));
-  IDD_CUDA(cudaEventCreateWithFlags(&ev_chunk, cudaEventDisableTiming));
+  const size_t need = 2 * xN + 2 * sN;
+  if (g->host_ws_elems < need) {
+    cudaFree(g->host_ws);
+    g->host_ws = nullptr;
+    g->host_ws_elems = 0;
+    IDD_CUDA(cudaMalloc((void**)&g->host_ws, need * sizeof(float)));
+    g->host_ws_elems = need;
+  }
+  struct Ws { float* p; } dX_in{g->host_ws}, dS_in{g->host_ws + xN}, dS_out{g->host_ws + xN + sN},
+      dX_out{g->host_ws + xN + 2 * sN};
+  for (int i = 0; i < 3; ++i) {
+    if (!g->host_streams[i]) IDD_CUDA(cudaStreamCreateWithFlags(&g->host_streams[i], cudaStreamNonBlocking));
+    if (!g->host_events[i]) IDD_CUDA(cudaEventCreateWithFlags(&g->host_events[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s_in = g->host_streams[0], s_cmp = g->host_streams[1], s_out = g->host_streams[2];
+  cudaEvent_t ev_x = g->host_events[0], ev_ds = g->host_events[1], ev_chunk = g->host_events[2];
   int rc = IDDGCN_OK;
   auto body = [&]() -> int {
     constexpr int NCHUNK = 8;
@@ -389,9 +548,7 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
     return IDDGCN_OK;
   };
   rc = body();
-  cudaDeviceSynchronize();
-  cudaEventDestroy(ev_x); cudaEventDestroy(ev_ds); cudaEventDestroy(ev_chunk);
-  cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out);
+  if (rc != IDDGCN_OK) cudaDeviceSynchronize();
   return rc;
 }
 

@@ -122,3 +122,19 @@ def test_bench_cpu_inputs_are_a_valid_graph():
     for k in struct:
         assert np.array_equal(struct[k], ref[k]), k
     assert nnz == ref["nnz"]
+
+
+def test_product_fold_pipeline_matches_oracle_and_shipped_files(golden_dir):
+    """tools/train_folds.fold_frames (host data prep of config 2) == oracle.fold_pipeline, which is pinned to the
+    shipped fold files by sha256 (test_oracle_pins)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_folds
+    from oracle import iddgcn_oracle as O
+    mine = train_folds.fold_frames(os.path.join(golden_dir, "data"))
+    ref = O.fold_pipeline(os.path.join(golden_dir, "data"))
+    for a, b in zip(mine, ref):
+        assert np.array_equal(a["X_train"], b["X_train"].values)
+        assert np.array_equal(a["X_test"], b["X_test"].values)
+        assert np.array_equal(a["neg_train"], b["X_train_neg"][0].astype(np.int64))
+        assert np.array_equal(a["neg_test"], b["neg_X_test"].values.astype(np.int64))

@@ -118,7 +118,16 @@ def main():
         procs = [ctx.Process(target=run_fold, args=(f, i % P, args, q)) for i, f in enumerate(wave)]
         for p in procs:
             p.start()
-        results += [q.get() for _ in wave]
+        got = 0
+        while got < len(wave):                     # never block on a child that died
+            try:
+                results.append(q.get(timeout=5))
+                got += 1
+            except Exception:
+                if any(p.exitcode not in (None, 0) for p in procs):
+                    for p in procs:
+                        p.terminate()
+                    raise SystemExit("a fold process failed")
         for p in procs:
             p.join()
     wall = time.perf_counter() - t0

@@ -221,6 +221,7 @@ def run_ours(args, wl):
         opts = dist.ProcessGroupNCCL.Options()
         opts.is_high_priority_stream = True
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        rs_group = dist.new_group(backend="nccl", pg_options=opts)   # second communicator: reduce-scatter stream
     R, D = wl["R"], wl["D"]
     if wl["scaling"] == "weak":
         N_total, per_rel_total = wl["N"] * world, wl["per_rel"] * world
@@ -244,7 +245,7 @@ def run_ours(args, wl):
     S = torch.empty((R, n_rows, D), device=dev)
     if world > 1:
         from iddgcn_b200.dist import PartitionedSpMM
-        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels)
+        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels, rs_group=rs_group)
         step = lambda: engine.step(X_local, dS, S)
         nnz_t = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
         dist.all_reduce(nnz_t)
@@ -389,7 +390,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--panels", type=int, default=4, help="column panels of the multi-GPU exchange pipeline")
+    ap.add_argument("--panels", type=int, default=2, help="column panels of the multi-GPU exchange pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

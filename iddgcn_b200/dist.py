@@ -45,15 +45,15 @@ def unpanelize(xp: torch.Tensor) -> torch.Tensor:
     return y.reshape(*lead, n, p * dc).contiguous()
 
 
-def _all_gather(out: torch.Tensor, inp: torch.Tensor, async_op: bool):
-    return dist.all_gather_into_tensor(out, inp, async_op=async_op)
+def _all_gather(out: torch.Tensor, inp: torch.Tensor, async_op: bool, group=None):
+    return dist.all_gather_into_tensor(out, inp, group=group, async_op=async_op)
 
 
-def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, rank: int, async_op: bool):
+def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, rank: int, async_op: bool, group=None):
     if dist.get_backend() == "nccl":
-        return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, async_op=async_op)
+        return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
     # host-logic path for the gloo tests (no reduce-scatter there): all-reduce, keep this rank's block
-    dist.all_reduce(inp, op=dist.ReduceOp.SUM)
+    dist.all_reduce(inp, op=dist.ReduceOp.SUM, group=group)
     n = out.shape[0]
     out.copy_(inp[rank * n:(rank + 1) * n])
     return None
@@ -61,11 +61,14 @@ def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, rank: int, async_op: b
 
 class PartitionedSpMM:
     def __init__(self, graph, D: int, world: int, rank: int, block: int, *, panels: int = 4, fwd_fn=None,
-                 bwd_fn=None, device=None):
+                 bwd_fn=None, device=None, ag_group=None, rs_group=None):
         if D % panels or (D // panels) % 4:
             raise ValueError(f"D={D} must split into {panels} panels whose width is a multiple of 4")
         self.g, self.D, self.world, self.rank, self.block, self.panels = graph, D, world, rank, block, panels
         self.Dc = D // panels
+        # two communicators (two NCCL streams): the all-gather is receive-heavy and the reduce-scatter send-heavy, so
+        # running them concurrently keeps both NVLink directions busy
+        self.ag_group, self.rs_group = ag_group, rs_group
         self.R = graph.R
         self.n_rows = graph.n_rows
         self.N_pad = block * world            # all-gather needs equal blocks; the last block may carry padding rows
@@ -97,21 +100,23 @@ class PartitionedSpMM:
 
     # -- one exchange + compute step -------------------------------------------------------------------
     def run_panels(self):
-        """all-gather -> fwd -> bwd -> reduce-scatter, pipelined over the column panels."""
+        """One step: backward panels feed the reduce-scatter while the all-gather feeds the forward panels.
+
+        Issue order on the compute stream is B0 F0 B1 F1 ...: backward panel c needs no exchange (dS is local), so its
+        kernel and the all-gather of panel c start together; its result goes straight into reduce-scatter c on the
+        second communicator while forward panel c consumes all-gather c."""
         P = self.panels
-        gathers = [_all_gather(self.Xp_full[c], self.Xp_local[c], async_op=True) for c in range(P)]
-        for c in range(P):
-            if gathers[c] is not None:
-                gathers[c].wait()
-            Xc = self.Xp_full[c][: self.g.N]
-            self.fwd_fn(self.g, Xc, self.Sp[c])
+        gathers = [_all_gather(self.Xp_full[c], self.Xp_local[c], True, self.ag_group) for c in range(P)]
         scatters = []
         for c in range(P):
             part = self.dXp_partial[c]
             self.bwd_fn(self.g, self.dSp[c], part[: self.g.N])
             if self.N_pad > self.g.N:
                 part[self.g.N:].zero_()
-            scatters.append(_reduce_scatter(self.dXp_local[c], part, self.rank, async_op=True))
+            scatters.append(_reduce_scatter(self.dXp_local[c], part, self.rank, True, self.rs_group))
+            if gathers[c] is not None:
+                gathers[c].wait()
+            self.fwd_fn(self.g, self.Xp_full[c][: self.g.N], self.Sp[c])
         for w in scatters:
             if w is not None:
                 w.wait()
@@ -149,10 +154,10 @@ class PartitionedSpMM:
             dist.barrier()
             a.record()
             for p in range(self.panels):
-                _all_gather(self.Xp_full[p], self.Xp_local[p], async_op=False)
+                _all_gather(self.Xp_full[p], self.Xp_local[p], False, self.ag_group)
             b.record()
             for p in range(self.panels):
-                _reduce_scatter(self.dXp_local[p], self.dXp_partial[p], self.rank, async_op=False)
+                _reduce_scatter(self.dXp_local[p], self.dXp_partial[p], self.rank, False, self.rs_group)
             c.record()
             torch.cuda.synchronize()
             out["all_gather"].append(a.elapsed_time(b))

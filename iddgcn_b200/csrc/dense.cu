@@ -86,17 +86,29 @@ __global__ void __launch_bounds__(GTHREADS)
   }
 }
 
-// C[b][m][n] (+)= sum_{s < splits} ws[b][s][m][n], ascending s
-__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N,
-                                     float* __restrict__ C, int64_t ldc, int64_t strideC, int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// C[b][m][n] (+)= sum_{s < splits} ws[b][s][m][n].  256 threads = 8 split-lanes x 32 consecutive outputs: split-lane j
+// sums partials j, j+8, ... in ascending order, then the 8 lane sums are added in ascending j (fixed order).
+__global__ void __launch_bounds__(256)
+    splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t MN, int64_t N, float* __restrict__ C,
+                         int64_t ldc, int64_t strideC, int accumulate) {
+  __shared__ float s_part[8][32];
+  const int o = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + o;
   const int b = blockIdx.y;
-  if (i >= MN) return;
-  const float* w = ws + (int64_t)b * splits * MN + i;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += w[(int64_t)k * MN];
-  float* c = C + (int64_t)b * strideC + (i / N) * ldc + (i % N);
-  *c = accumulate ? (*c + s) : s;
+  if (i < MN) {
+    const float* w = ws + (int64_t)b * splits * MN + i;
+    for (int k = j; k < splits; k += 8) s += w[(int64_t)k * MN];
+  }
+  s_part[j][o] = s;
+  __syncthreads();
+  if (j == 0 && i < MN) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += s_part[q][o];
+    float* c = C + (int64_t)b * strideC + (i / N) * ldc + (i % N);
+    *c = accumulate ? (*c + t) : t;
+  }
 }
 
 int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA,
@@ -154,7 +166,7 @@ int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
   gemm_tile_kernel<true, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, workspace, N,
                                                           (int64_t)splits * MN, 0, chunk, MN);
   IDD_LAUNCH_CHECK();
-  dim3 rgrid((unsigned)((MN + 255) / 256), (unsigned)batch);
+  dim3 rgrid((unsigned)((MN + 31) / 32), (unsigned)batch);
   splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(workspace, splits, MN, N, C, ldc, strideC, accumulate ? 1 : 0);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;

@@ -48,3 +48,9 @@ struct iddgcn_plan {
   int32_t* by_rel_perm = nullptr;   // [T]
   int32_t* by_rel_ptr = nullptr;    // [R+1]
 };
+
+namespace iddgcn {
+// new plan holding the triples of `a` followed by those of `b` (same N, R); caller owns it (plan_destroy_internal)
+int plan_concat(const iddgcn_plan* a, const iddgcn_plan* b, cudaStream_t st, iddgcn_plan** out);
+void plan_destroy_internal(iddgcn_plan* p);
+}  // namespace iddgcn

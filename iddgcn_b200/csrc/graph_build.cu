@@ -387,6 +387,39 @@ static void plan_free(iddgcn_plan* p) {
   delete p;
 }
 
+__global__ void widen_concat_kernel(const int32_t* __restrict__ a, size_t na, const int32_t* __restrict__ b, size_t nb,
+                                    int64_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na + nb) return;
+  out[i] = i < na ? (int64_t)a[i] : (int64_t)b[i - na];
+}
+
+int plan_concat(const iddgcn_plan* a, const iddgcn_plan* b, cudaStream_t st, iddgcn_plan** out) {
+  IDD_CHECK(a && b && out && a->N == b->N && a->R == b->R, IDDGCN_EINVAL, "plans do not match");
+  const size_t na = (size_t)a->T, nb = (size_t)b->T, n = na + nb;
+  DevBuf<int64_t> tmp;
+  IDD_CUDA(tmp.ensure(3 * (n ? n : 1)));
+  if (n) {
+    widen_concat_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->head, na, b->head, nb, tmp.p);
+    IDD_LAUNCH_CHECK();
+    widen_concat_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->rel, na, b->rel, nb, tmp.p + n);
+    IDD_LAUNCH_CHECK();
+    widen_concat_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a->tail, na, b->tail, nb, tmp.p + 2 * n);
+    IDD_LAUNCH_CHECK();
+  }
+  iddgcn_plan* p = new iddgcn_plan();
+  int rc = plan_create_impl(tmp.p, tmp.p + n, tmp.p + 2 * n, (int64_t)n, 1, a->N, a->R, st, p);
+  if (rc != IDDGCN_OK) {
+    plan_free(p);
+    return rc;
+  }
+  IDD_CUDA(cudaStreamSynchronize(st));
+  *out = p;
+  return IDDGCN_OK;
+}
+
+void plan_destroy_internal(iddgcn_plan* p) { plan_free(p); }
+
 }  // namespace iddgcn
 
 using namespace iddgcn;

@@ -56,6 +56,9 @@ struct iddgcn_model {
   float *S = nullptr, *Z = nullptr, *dZ = nullptr, *dS = nullptr;
   DevBuf<float> gemm_ws, small_ws, y_all, dy_all;
   std::unordered_map<const iddgcn_plan*, TripleWS> ws;
+  // positives and negatives of a train step run as ONE batch of triples: (pos, neg) -> concatenated plan
+  struct Merged { const iddgcn_plan* pos; const iddgcn_plan* neg; iddgcn_plan* both; };
+  std::vector<Merged> merged;
   // captured training step
   cudaGraphExec_t graph_exec = nullptr;
   const void* graph_key[3] = {nullptr, nullptr, nullptr};
@@ -92,6 +95,7 @@ static void model_free(iddgcn_model* m) {
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   for (auto& kv : m->ws) kv.second.release();
+  for (auto& e : m->merged) plan_destroy_internal(e.both);
   cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v);
   cudaFree(m->step_dev); cudaFree(m->loss_dev);
   cudaFree(m->S); cudaFree(m->Z); cudaFree(m->dZ); cudaFree(m->dS);
@@ -228,18 +232,18 @@ static int node_backward(iddgcn_model* m, const iddgcn_graph* g, const float* va
   return IDDGCN_OK;
 }
 
-static int train_step_body(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* pos, const iddgcn_plan* neg,
-                           TripleWS* wp, TripleWS* wn, float lr, float b1, float b2, float eps, int64_t step,
-                           bool step_on_device, int apply_update, float* loss_out, float* y_out, cudaStream_t st) {
-  const int64_t Tp = pos->T, Tn = neg ? neg->T : 0, Tt = Tp + Tn;
+// One batch holds the positives followed by the negatives (same parameters, same graph): every per-triple kernel
+// runs once per step instead of twice; only the loss distinguishes the two halves (labels by position).
+static int train_step_body(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* both, int64_t Tp, TripleWS* w,
+                           float lr, float b1, float b2, float eps, int64_t step, bool step_on_device,
+                           int apply_update, float* loss_out, float* y_out, cudaStream_t st) {
+  const int64_t Tt = both->T;
   IDD_TRY(zero_step_buffers(m, true, st));
   IDD_TRY(node_forward(m, g, nullptr, IDDGCN_VALS_ONES, st));
-  IDD_TRY(triple_forward(m, pos, wp, m->y_all.p, st));                       // IDDGCN.py:147-153
-  if (neg) IDD_TRY(triple_forward(m, neg, wn, m->y_all.p + Tp, st));         // IDDGCN.py:154-160
+  IDD_TRY(triple_forward(m, both, w, m->y_all.p, st));                       // IDDGCN.py:147-160
   // y_pred = concat, y_true = [1..1 | 0..0], loss = BCE; loss *= 1/N  (IDDGCN.py:161-168)
   IDD_TRY(bce_loss_grad(m->y_all.p, Tp, Tt, 1.0f / (float)m->N, m->dy_all.p, m->loss_dev, m->small_ws.p, st));
-  IDD_TRY(triple_backward(m, pos, wp, m->y_all.p, m->dy_all.p, st));
-  if (neg) IDD_TRY(triple_backward(m, neg, wn, m->y_all.p + Tp, m->dy_all.p + Tp, st));
+  IDD_TRY(triple_backward(m, both, w, m->y_all.p, m->dy_all.p, st));
   IDD_TRY(node_backward(m, g, nullptr, IDDGCN_VALS_ONES, nullptr, st));
   if (apply_update) {
     if (step_on_device) IDD_TRY(increment_counter(m->step_dev, st));
@@ -252,19 +256,29 @@ static int train_step_body(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_
 }
 
 static int prepare_train(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_plan* pos, const iddgcn_plan* neg,
-                         TripleWS** wp, TripleWS** wn) {
+                         cudaStream_t st, const iddgcn_plan** both, TripleWS** w) {
   IDD_TRY(check_compat(m, g, pos));
   if (neg) IDD_TRY(check_compat(m, g, neg));
   IDD_CHECK(pos->T + (neg ? neg->T : 0) > 0, IDDGCN_EINVAL, "train step needs at least one triple");
-  IDD_TRY(ensure_triple_ws(m, pos, wp));
-  *wn = nullptr;
-  if (neg) IDD_TRY(ensure_triple_ws(m, neg, wn));
-  const size_t Tt = (size_t)(pos->T + (neg ? neg->T : 0));
+  const iddgcn_plan* b = pos;
+  if (neg && neg->T > 0) {
+    b = nullptr;
+    for (auto& e : m->merged)
+      if (e.pos == pos && e.neg == neg && e.both->T == pos->T + neg->T) b = e.both;
+    if (!b) {
+      iddgcn_plan* np = nullptr;
+      IDD_TRY(plan_concat(pos, neg, st, &np));
+      m->merged.push_back({pos, neg, np});
+      b = np;
+    }
+  }
+  IDD_TRY(ensure_triple_ws(m, b, w));
+  const size_t Tt = (size_t)b->T;
   if (Tt > m->y_all.n) IDD_CUDA(m->y_all.ensure(Tt));
   if (Tt > m->dy_all.n) IDD_CUDA(m->dy_all.ensure(Tt));
   const size_t bs = bce_scratch_elems((int64_t)Tt);
   if (bs > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(bs));
-  // ensure_triple_ws may have re-allocated the shared scratch: refresh pointers kept by callers (none are cached)
+  *both = b;
   return IDDGCN_OK;
 }
 
@@ -349,6 +363,17 @@ int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p) {
     it->second.release();
     m->ws.erase(it);
   }
+  for (size_t i = 0; i < m->merged.size();) {
+    if (m->merged[i].pos == p || m->merged[i].neg == p) {
+      cudaDeviceSynchronize();
+      auto it2 = m->ws.find(m->merged[i].both);
+      if (it2 != m->ws.end()) { it2->second.release(); m->ws.erase(it2); }
+      plan_destroy_internal(m->merged[i].both);
+      m->merged.erase(m->merged.begin() + i);
+    } else {
+      ++i;
+    }
+  }
   if (m->graph_exec && (m->graph_key[1] == p || m->graph_key[2] == p)) {
     cudaGraphExecDestroy(m->graph_exec);
     m->graph_exec = nullptr;
@@ -387,10 +412,11 @@ int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddg
 int iddgcn_model_train_step(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* pos,
                             const iddgcn_plan_t* neg, float lr, float beta1, float beta2, float eps,
                             int64_t step_index, int apply_update, float* loss_out, float* y_out, void* stream) {
-  TripleWS *wp, *wn;
-  IDD_TRY(prepare_train(m, g, pos, neg, &wp, &wn));
+  TripleWS* w;
+  const iddgcn_plan* both;
+  IDD_TRY(prepare_train(m, g, pos, neg, (cudaStream_t)stream, &both, &w));
   IDD_CHECK(step_index >= 1 || !apply_update, IDDGCN_EINVAL, "Adam step_index starts at 1");
-  return train_step_body(m, g, pos, neg, wp, wn, lr, beta1, beta2, eps, step_index, false, apply_update, loss_out,
+  return train_step_body(m, g, both, pos->T, w, lr, beta1, beta2, eps, step_index, false, apply_update, loss_out,
                          y_out, (cudaStream_t)stream);
 }
 
@@ -401,8 +427,6 @@ int iddgcn_model_train_step(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
 int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* pos,
                             const iddgcn_plan_t* neg, float lr, float beta1, float beta2, float eps,
                             int64_t first_step_index, int64_t num_steps, float* loss_history, void* stream) {
-  TripleWS *wp, *wn;
-  IDD_TRY(prepare_train(m, g, pos, neg, &wp, &wn));
   IDD_CHECK(first_step_index >= 1 && num_steps >= 0, IDDGCN_EINVAL, "bad step range");
   cudaStream_t st = (cudaStream_t)stream;
   bool own = false;
@@ -412,6 +436,9 @@ int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
     st = m->own_stream;
     own = true;
   }
+  TripleWS* w;
+  const iddgcn_plan* both;
+  IDD_TRY(prepare_train(m, g, pos, neg, st, &both, &w));
   const int64_t t0 = first_step_index - 1;  // the graph increments the counter before Adam reads it
   IDD_CUDA(cudaMemcpyAsync(m->step_dev, &t0, sizeof(int64_t), cudaMemcpyHostToDevice, st));
   IDD_CUDA(cudaStreamSynchronize(st));
@@ -422,7 +449,7 @@ int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     IDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = train_step_body(m, g, pos, neg, wp, wn, lr, beta1, beta2, eps, 0, true, 1, nullptr, nullptr, st);
+    int rc = train_step_body(m, g, both, pos->T, w, lr, beta1, beta2, eps, 0, true, 1, nullptr, nullptr, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != IDDGCN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     IDD_CUDA(ce);

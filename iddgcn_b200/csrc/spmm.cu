@@ -388,14 +388,18 @@ static int launch_stream(const StreamArgs& a, int mode, cudaStream_t st) {
   return launch_stream_mode<32, USE_PERM>(a, mode, st);
 }
 
-// IDDGCN_SPMM_V1=1 selects the v1 (row-at-a-time) kernels for A/B measurements; D > 128 always uses v1.
-static bool use_v1() {
-  static int cached = -1;
-  if (cached < 0) {
+// Kernel choice.  v2 gives every warp 32 consecutive rows, so it needs >= ~64k rows to fill 148 SMs; below that (the
+// shipped 845-node graph, explainer sub-graphs) the row-at-a-time v1 kernel exposes 32/LPR times more parallelism and
+// is the faster one.  D > 128 always uses v1.  IDDGCN_SPMM_V1=1 / =0 forces v1 / v2 for A/B measurements.
+constexpr int64_t V2_MIN_ROWS = 65536;
+static bool use_v1(int64_t rows) {
+  static int forced = -2;
+  if (forced == -2) {
     const char* e = getenv("IDDGCN_SPMM_V1");
-    cached = (e && e[0] == '1') ? 1 : 0;
+    forced = !e ? -1 : (e[0] == '1' ? 1 : 0);
   }
-  return cached == 1;
+  if (forced >= 0) return forced == 1;
+  return rows < V2_MIN_ROWS;
 }
 
 static int check_common(const iddgcn_graph* g, int64_t D, const float* vals, int mode) {
@@ -412,7 +416,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
                    int64_t row_begin, int64_t row_end, cudaStream_t st) {
-  if (D <= 128 && !use_v1()) {
+  if (D <= 128 && !use_v1((int64_t)g->R * g->n_rows)) {
     StreamArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, (int)(D / 4), 0};
     return launch_stream<false>(a, mode, st);
   }
@@ -422,7 +426,7 @@ int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float
 
 int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
                      int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st) {
-  if (D <= 128 && !use_v1()) {
+  if (D <= 128 && !use_v1(g->N)) {
     StreamArgs a{g->bwd_rowptr, g->bwd_src, g->bwd_perm, vals, dS, dX, row_begin, row_end, (int)(D / 4), accumulate};
     return launch_stream<true>(a, mode, st);
   }

@@ -240,19 +240,22 @@ int layer_bwd_post(const float* dz, const float* W_alpha, int64_t T, int64_t D, 
 
 // ---------------------------------------------------------------------------------------------
 // segment sums over the plan's by-head / by-tail orderings (gather backward without atomics)
-template <int NV, bool GATED>
+template <int NV, bool GATED, int RCMAX>
 __global__ void __launch_bounds__(TW * 32)
     segment_scatter_kernel(const int32_t* __restrict__ ptr_h, const int32_t* __restrict__ perm_h,
                            const int32_t* __restrict__ ptr_t, const int32_t* __restrict__ perm_t,
                            const float4* __restrict__ dP, const float* __restrict__ alpha, int64_t T, int64_t N,
                            int nvec, int R, float4* __restrict__ out, int accumulate) {
   const int lane = threadIdx.x & 31;
+  // relations accumulated per sweep over the node's triples (fewer at large D to bound registers).  blockIdx.y picks
+  // a group of RC relations: with RCMAX = 1 (small N) every (node, relation) pair gets its own warp.
+  constexpr int RC = GATED ? (RCMAX < (NV >= 4 ? 2 : 4) ? RCMAX : (NV >= 4 ? 2 : 4)) : 1;
   const int64_t n = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
   if (n >= N) return;
-  // relations accumulated per sweep over the node's triples (fewer at large D to bound registers)
-  constexpr int RC = GATED ? (NV >= 4 ? 2 : 4) : 1;
   const int planes = GATED ? R : 1;
-  for (int r0 = 0; r0 < planes; r0 += RC) {
+  const int r_first = blockIdx.y * RC * (int)((planes + RC * gridDim.y - 1) / (RC * gridDim.y));
+  const int r_last = (blockIdx.y + 1) * RC * (int)((planes + RC * gridDim.y - 1) / (RC * gridDim.y));
+  for (int r0 = r_first; r0 < planes && r0 < r_last; r0 += RC) {
     // Kahan-compensated sums: a hub node can own thousands of triples, and a plain sequential fp32 sum of that
     // many terms is what would break the 1e-5 gradient tolerance.
     float4 acc[RC][NV], cmp[RC][NV];
@@ -336,17 +339,26 @@ int segment_scatter(const iddgcn_plan* p, const float* dP, const float* alpha, i
                     cudaStream_t st) {
   IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
   const int nvec = (int)(D / 4);
-  const unsigned grid = (unsigned)((p->N + TW - 1) / TW);
+  const unsigned gx = (unsigned)((p->N + TW - 1) / TW);
+  // few nodes (the shipped graph has 845): one warp per (node, relation) instead of per node
+  const bool split_rel = alpha != nullptr && p->N < 32768 && p->R > 1;
+  const dim3 grid(gx, split_rel ? (unsigned)p->R : 1u);
 #define IDD_ARGS p->by_head_ptr, p->by_head_perm, p->by_tail_ptr, p->by_tail_perm, reinterpret_cast<const float4*>(dP), \
                  alpha, p->T, p->N, nvec, p->R, reinterpret_cast<float4*>(out), accumulate
   if (alpha) {
-    if (nvec <= 32) segment_scatter_kernel<1, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-    else if (nvec <= 64) segment_scatter_kernel<2, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-    else segment_scatter_kernel<4, true><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    if (split_rel) {
+      if (nvec <= 32) segment_scatter_kernel<1, true, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      else if (nvec <= 64) segment_scatter_kernel<2, true, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      else segment_scatter_kernel<4, true, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    } else {
+      if (nvec <= 32) segment_scatter_kernel<1, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      else if (nvec <= 64) segment_scatter_kernel<2, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      else segment_scatter_kernel<4, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    }
   } else {
-    if (nvec <= 32) segment_scatter_kernel<1, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-    else if (nvec <= 64) segment_scatter_kernel<2, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-    else segment_scatter_kernel<4, false><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    if (nvec <= 32) segment_scatter_kernel<1, false, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else if (nvec <= 64) segment_scatter_kernel<2, false, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+    else segment_scatter_kernel<4, false, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
   }
 #undef IDD_ARGS
   IDD_LAUNCH_CHECK();

@@ -393,12 +393,8 @@ static int launch_stream(const StreamArgs& a, int mode, cudaStream_t st) {
 // is the faster one.  D > 128 always uses v1.  IDDGCN_SPMM_V1=1 / =0 forces v1 / v2 for A/B measurements.
 constexpr int64_t V2_MIN_ROWS = 65536;
 static bool use_v1(int64_t rows) {
-  static int forced = -2;
-  if (forced == -2) {
-    const char* e = getenv("IDDGCN_SPMM_V1");
-    forced = !e ? -1 : (e[0] == '1' ? 1 : 0);
-  }
-  if (forced >= 0) return forced == 1;
+  const char* e = getenv("IDDGCN_SPMM_V1");  // read on every call so tests can flip it at run time
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
   return rows < V2_MIN_ROWS;
 }
 

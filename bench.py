@@ -272,10 +272,14 @@ def run_ours(args, wl):
     # A timed region of K x 3 ms is shorter than nvidia-smi's sampling period, so the clock sampler first watches
     # ~0.5 s of the same step (untimed, extra warm-up) and keeps running through the timed region that follows.
     t_load = time.perf_counter()
-    while time.perf_counter() - t_load < 0.5:
-        for _ in range(10):
-            step()
-        torch.cuda.synchronize()
+    step()
+    torch.cuda.synchronize()
+    est = torch.tensor([time.perf_counter() - t_load], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)        # every rank must run the same number of steps
+    n_load = int(min(300, max(5, 0.5 / max(float(est.item()), 1e-4))))
+    for _ in range(n_load):
+        step()
     barrier()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

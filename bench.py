@@ -35,6 +35,8 @@ WORKLOADS = {
     "c3": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak"),
     "c4": dict(N=20_000_000, R=2, per_rel=100_000_000, D=128, scaling="strong"),
     "small": dict(N=100_000, R=2, per_rel=1_000_000, D=128, scaling="weak"),
+    # skewed variant of c3: destination degrees ~ Zipf(s=1.2), same raw edge count
+    "c3zipf": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak", zipf=1.2),
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -107,7 +109,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed):
+def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed, zipf=None):
     """Uniform random directed edges (SURVEY §8d recipe, generated on device): per relation
     per_rel_total (head, tail) pairs; a rank keeps only heads inside its row block."""
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -118,7 +120,15 @@ def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed):
         left = per_rel_total
         while left > 0:
             n = min(chunk, left)
-            h = torch.randint(0, N_total, (n,), device=dev, generator=gen)
+            if zipf:   # inverse-CDF sampling of rank k with p(k) ~ k^-s, ranks scattered by a fixed permutation
+                if r == 0 and left == per_rel_total:
+                    w = torch.arange(1, N_total + 1, device=dev, dtype=torch.float64).pow(-float(zipf))
+                    cdf = torch.cumsum(w, 0) / w.sum()
+                    scatter = torch.randperm(N_total, device=dev, generator=gen)
+                u = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
+                h = scatter[torch.searchsorted(cdf, u).clamp_(max=N_total - 1)]
+            else:
+                h = torch.randint(0, N_total, (n,), device=dev, generator=gen)
             t = torch.randint(0, N_total, (n,), device=dev, generator=gen)
             if row_lo != 0 or row_hi != N_total:
                 keep = (h >= row_lo) & (h < row_hi)
@@ -231,7 +241,7 @@ def run_ours(args, wl):
     row_lo, row_hi = rank * block, min((rank + 1) * block, N_total)
     n_rows = row_hi - row_lo
 
-    tri = make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed=7)
+    tri = make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed=7, zipf=wl.get("zipf"))
     t0 = time.perf_counter()
     g = Graph(tri, N_total, R, row_block=(row_lo, row_hi))
     torch.cuda.synchronize()
@@ -377,7 +387,7 @@ def run_ours(args, wl):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        if wl["per_rel"] <= 20_000_000:
+        if wl["per_rel"] <= 20_000_000 and not wl.get("zipf"):
             # the very graph and inputs the GPU just ran, exported through the C ABI
             struct = g.export()
             cN, cn_rows, cnnz = N_total, n_rows, nnz_local
@@ -430,6 +440,7 @@ def main():
               "xP row-partitioned at --gpus P (configs[3] recipe, weak)",
         "c4": "synthetic 20M-node / 200M-edge 2-relation graph, D=128, destination-row partitioned (configs[3])",
         "small": "synthetic 100k-node / 2M-edge 2-relation graph, D=128 (smoke size)",
+        "c3zipf": "config-3 shape with Zipf(1.2) destination degrees (skewed variant, SURVEY 8d)",
     }[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

@@ -3,6 +3,8 @@
 #include <vector>
 #include "common.cuh"
 
+constexpr int HEAVY_EDGES = 1024;
+
 struct iddgcn_graph {
   int device = 0;
   int64_t N = 0;        // source nodes (columns)
@@ -22,6 +24,17 @@ struct iddgcn_graph {
   int32_t* bwd_rowptr = nullptr;  // [N+1]
   int32_t* bwd_src = nullptr;     // [nnz]  r·n_rows + local head
   int32_t* bwd_perm = nullptr;    // [nnz]  CSR edge id
+  // Hub rows (more than HEAVY_EDGES edges) are skipped by the row kernels and handled by a split pass: the row is cut
+  // into segments of HEAVY_EDGES edges summed by separate warps, then combined in ascending segment order.
+  struct HeavyList {
+    int H = 0;                    // number of hub rows
+    int total_segs = 0;
+    int32_t* rows = nullptr;      // [H]   row ids, ascending
+    int32_t* segptr = nullptr;    // [H+1] first segment of each hub row
+  };
+  HeavyList heavy_fwd, heavy_bwd;
+  mutable float* heavy_ws = nullptr;   // [total_segs, D] partial sums (grown on demand, never inside a stream capture)
+  mutable size_t heavy_ws_elems = 0;
   float* rel_sums_scratch = nullptr;
   // lazily created by iddgcn_spmm_fwd_bwd_host and kept for the next call (mutable cache)
   mutable float* host_ws = nullptr;

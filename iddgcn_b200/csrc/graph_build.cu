@@ -126,7 +126,60 @@ __global__ void bwd_fill_kernel(const int32_t* __restrict__ csc_rowptr, const in
   }
 }
 
+// hub-row detection: flag[i] = number of HEAVY_EDGES-segments of row i if it is a hub row, else 0; hub[i] = 0/1
+__global__ void heavy_flag_kernel(const int32_t* __restrict__ ptr, size_t rows, uint32_t* __restrict__ is_hub,
+                                  uint32_t* __restrict__ nseg) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > rows) return;
+  uint32_t h = 0, s = 0;
+  if (i < rows) {
+    const int deg = ptr[i + 1] - ptr[i];
+    if (deg > HEAVY_EDGES) { h = 1; s = (uint32_t)((deg + HEAVY_EDGES - 1) / HEAVY_EDGES); }
+  }
+  is_hub[i] = h;
+  nseg[i] = s;
+}
+
+__global__ void heavy_compact_kernel(const int32_t* __restrict__ ptr, size_t rows, const uint32_t* __restrict__ hub_pos,
+                                     const uint32_t* __restrict__ seg_pos, int32_t* __restrict__ out_rows,
+                                     int32_t* __restrict__ out_segptr, uint32_t H) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > rows) return;
+  if (i == rows) { out_segptr[H] = (int32_t)seg_pos[rows]; return; }
+  if (ptr[i + 1] - ptr[i] > HEAVY_EDGES) {
+    out_rows[hub_pos[i]] = (int32_t)i;
+    out_segptr[hub_pos[i]] = (int32_t)seg_pos[i];
+  }
+}
+
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static inline unsigned blocks_for(size_t n, int threads);
+
+static int build_heavy_list(const int32_t* ptr, size_t rows, cudaStream_t st, iddgcn_graph::HeavyList* out) {
+  DevBuf<uint32_t> hub, seg, scr;
+  IDD_CUDA(hub.ensure(rows + 1));
+  IDD_CUDA(seg.ensure(rows + 1));
+  IDD_CUDA(scr.ensure(scan_scratch_elems(rows + 1)));
+  heavy_flag_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub.p, seg.p);
+  IDD_LAUNCH_CHECK();
+  IDD_TRY(exclusive_scan_u32(hub.p, hub.p, rows + 1, scr.p, st));
+  IDD_TRY(exclusive_scan_u32(seg.p, seg.p, rows + 1, scr.p, st));
+  uint32_t H = 0, S = 0;
+  IDD_CUDA(cudaMemcpyAsync(&H, hub.p + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaMemcpyAsync(&S, seg.p + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaStreamSynchronize(st));
+  out->H = (int)H;
+  out->total_segs = (int)S;
+  if (H) {
+    IDD_CUDA(cudaMalloc((void**)&out->rows, (size_t)H * sizeof(int32_t)));
+    IDD_CUDA(cudaMalloc((void**)&out->segptr, ((size_t)H + 1) * sizeof(int32_t)));
+    heavy_compact_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub.p, seg.p, out->rows, out->segptr, H);
+    IDD_LAUNCH_CHECK();
+    IDD_CUDA(cudaStreamSynchronize(st));
+  }
+  return IDDGCN_OK;
+}
 
 static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device, int64_t N, int R, int64_t row_lo,
                             int64_t row_hi, cudaStream_t st, iddgcn_graph* g) {
@@ -250,6 +303,8 @@ static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device,
     }
     IDD_CUDA(cudaStreamSynchronize(st));  // scr2 is freed at the end of this scope
   }
+  IDD_TRY(build_heavy_list(g->csr_rowptr, csr_segs, st, &g->heavy_fwd));
+  IDD_TRY(build_heavy_list(g->bwd_rowptr, (size_t)N, st, &g->heavy_bwd));
   g->nnz = (int64_t)nnz;
   // per-relation counts: R+1 strided reads of the CSR row pointer
   std::vector<int32_t> bounds(R + 1, 0);
@@ -267,6 +322,9 @@ static void graph_free(iddgcn_graph* g) {
   cudaFree(g->csc_rowptr); cudaFree(g->csc_row); cudaFree(g->csc_perm);
   cudaFree(g->bwd_rowptr); cudaFree(g->bwd_src); cudaFree(g->bwd_perm);
   cudaFree(g->rel_sums_scratch);
+  cudaFree(g->heavy_fwd.rows); cudaFree(g->heavy_fwd.segptr);
+  cudaFree(g->heavy_bwd.rows); cudaFree(g->heavy_bwd.segptr);
+  cudaFree(g->heavy_ws);
   cudaFree(g->host_ws);
   for (int i = 0; i < 3; ++i) {
     if (g->host_streams[i]) cudaStreamDestroy(g->host_streams[i]);

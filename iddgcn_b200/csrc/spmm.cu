@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     gather_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
                        const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
-                       int G, int64_t seg_stride, int64_t src_group_rows, int nvec /* D/4 */, int accumulate) {
+                       int G, int64_t seg_stride, int64_t src_group_rows, int nvec /* D/4 */, int accumulate,
+                       int heavy_t) {
   constexpr int SUBS = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     const int64_t s = (int64_t)gi * seg_stride + o;
     const int beg = ld_stream_i32(ptr + s);
     const int end = ld_stream_i32(ptr + s + 1);
+    if (end - beg > heavy_t) return;  // hub row: written by the split pass (only used with G == 1)
     const float4* __restrict__ sbase = reinterpret_cast<const float4*>(src + (size_t)gi * src_group_rows * D);
     for (int base = beg; base < end; base += LPR) {
       const int my_e = base + l;
@@ -125,12 +127,12 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 // backward: ptr=bwd_rowptr, idx=bwd_src,  src=dS as [(R·n_rows),D], weight index perm[e]
 constexpr int SLAB = 512;  // staged indices per warp
 
-template <int LPR, int U, int MODE, bool USE_PERM>
+template <int LPR, int U, int MODE, bool USE_PERM, bool HUBS>
 __global__ void __launch_bounds__(SPMM_THREADS)
     stream_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
                        const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
-                       int nvec, int accumulate) {
+                       int nvec, int accumulate, int heavy_t) {
   constexpr int SUBS = 32 / LPR;
   constexpr int SUB_SLAB = SLAB / SUBS;
   constexpr bool WEIGHTED = MODE != IDDGCN_VALS_ONES;
@@ -154,84 +156,262 @@ __global__ void __launch_bounds__(SPMM_THREADS)
   const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
   float4* __restrict__ out4 = reinterpret_cast<float4*>(out) + (size_t)r0 * nvec;
 
-  int row = 0;
-  int cur_end = __shfl_sync(mask, my_end, 0, LPR);
-  int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (!HUBS) {
+    // graph without hub rows: the tight loop (no per-row degree test)
+    int row = 0;
+    int cur_end = __shfl_sync(mask, my_end, 0, LPR);
+    int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto flush = [&]() {
-    if (l < nvec) {
-      float4 r = acc;
-      float4* o = out4 + (size_t)row * nvec + l;
-      if (accumulate) {
-        const float4 prev = *o;
-        r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+    auto flush = [&]() {
+      if (l < nvec) {
+        float4 r = acc;
+        float4* o = out4 + (size_t)row * nvec + l;
+        if (accumulate) {
+          const float4 prev = *o;
+          r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+        }
+        st_stream_f4(o, r);
       }
-      st_stream_f4(o, r);
-    }
-    acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    ++row;
-    cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
-    if (row >= nrows) cur_end = 0x7fffffff;
-  };
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      ++row;
+      cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
+      if (row >= nrows) cur_end = 0x7fffffff;
+    };
 
-  while (pos < chunk_end) {
-    if (pos + U > slab_hi && slab_hi < chunk_end) {  // refill the slab starting at the current position
-      __syncwarp(mask);
-      slab_lo = pos;
-      slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
-      for (int q = l; q < slab_hi - slab_lo; q += LPR) {
-        const int e = slab_lo + q;
-        sl_idx[q] = ld_stream_i32(idx + e);
-        if (WEIGHTED) sl_w[q] = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + e) : e);
+    while (pos < chunk_end) {
+      if (pos + U > slab_hi && slab_hi < chunk_end) {  // refill the slab starting at the current position
+        __syncwarp(mask);
+        slab_lo = pos;
+        slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
+        for (int q = l; q < slab_hi - slab_lo; q += LPR) {
+          const int e = slab_lo + q;
+          sl_idx[q] = ld_stream_i32(idx + e);
+          if (WEIGHTED) sl_w[q] = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + e) : e);
+        }
+        __syncwarp(mask);
       }
-      __syncwarp(mask);
-    }
-    const int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
-    float4 v[U];
-    float w[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u < n) {
-        const int sidx = sl_idx[pos + u - slab_lo];
-        if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
-        v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (u < n) {
-        while (cur_end == pos + u) flush();
-        if (WEIGHTED) {
-          acc.x = fmaf(w[u], v[u].x, acc.x); acc.y = fmaf(w[u], v[u].y, acc.y);
-          acc.z = fmaf(w[u], v[u].z, acc.z); acc.w = fmaf(w[u], v[u].w, acc.w);
-        } else {
-          acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      const int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
+      float4 v[U];
+      float w[U];
+  #pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < n) {
+          const int sidx = sl_idx[pos + u - slab_lo];
+          if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
+          v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+  #pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < n) {
+          while (cur_end == pos + u) flush();
+          if (WEIGHTED) {
+            acc.x = fmaf(w[u], v[u].x, acc.x); acc.y = fmaf(w[u], v[u].y, acc.y);
+            acc.z = fmaf(w[u], v[u].z, acc.z); acc.w = fmaf(w[u], v[u].w, acc.w);
+          } else {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          }
+        }
+      }
+      pos += n;
     }
-    pos += n;
+    while (row < nrows) flush();
+  } else {
+    int row = 0, row_beg = chunk_beg;
+    int cur_end = __shfl_sync(mask, my_end, 0, LPR);
+    bool heavy = cur_end - row_beg > heavy_t;  // hub rows are skipped here and written by the split pass
+    int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto store_row = [&]() {
+      if (l < nvec) {
+        float4 r = acc;
+        float4* o = out4 + (size_t)row * nvec + l;
+        if (accumulate) {
+          const float4 prev = *o;
+          r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+        }
+        st_stream_f4(o, r);
+      }
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto next_row = [&]() {
+      row_beg = cur_end;
+      ++row;
+      cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
+      heavy = false;
+      if (row >= nrows) cur_end = 0x7fffffff;
+      else heavy = cur_end - row_beg > heavy_t;
+    };
+
+    while (row < nrows) {
+      if (heavy) {  // jump over the hub row's edges
+        pos = cur_end;
+        next_row();
+        continue;
+      }
+      if (pos == cur_end) {  // row complete (or empty)
+        store_row();
+        next_row();
+        continue;
+      }
+      if (pos + U > slab_hi && slab_hi < chunk_end) {  // refill the slab starting at the current position
+        __syncwarp(mask);
+        slab_lo = pos;
+        slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
+        for (int q = l; q < slab_hi - slab_lo; q += LPR) {
+          const int e = slab_lo + q;
+          sl_idx[q] = ld_stream_i32(idx + e);
+          if (WEIGHTED) sl_w[q] = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + e) : e);
+        }
+        __syncwarp(mask);
+      }
+      const int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
+      float4 v[U];
+      float w[U];
+  #pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < n) {
+          const int sidx = sl_idx[pos + u - slab_lo];
+          if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
+          v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      int consumed = 0;
+      bool stop = false;
+  #pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < n && !stop) {
+          if (pos + u == cur_end) {  // the stream crosses into the next row(s)
+            store_row();
+            next_row();
+            while (row < nrows && !heavy && cur_end == pos + u) {  // empty rows
+              store_row();
+              next_row();
+            }
+            stop = heavy || row >= nrows;  // a hub row starts here: drop the rest of this batch
+          }
+          if (!stop) {
+            if (WEIGHTED) {
+              acc.x = fmaf(w[u], v[u].x, acc.x); acc.y = fmaf(w[u], v[u].y, acc.y);
+              acc.z = fmaf(w[u], v[u].z, acc.z); acc.w = fmaf(w[u], v[u].w, acc.w);
+            } else {
+              acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            }
+            ++consumed;
+          }
+        }
+      }
+      pos += consumed;
+    }
   }
-  while (row < nrows) flush();
 }
 
-// SDDMM: dvals[e] = <dS[seg(e), :], X[col[e], :]> (· σ'(vals[e]) in SIGMOID mode), CSR edge order.
-template <int LPR, int CH, int U, int MODE>
+// ---------------------------------------------------------------------------------------------
+// Split pass for hub rows (degree > HEAVY_EDGES): one lane slice per HEAVY_EDGES-edge segment writes a partial sum,
+// then one slice per hub row adds its partials in ascending segment order.  Deterministic; runs only when the graph
+// has hub rows (none in the uniform benchmark graphs, many in Zipf-skewed ones).
+template <int LPR, int CH, int U, int MODE, bool USE_PERM>
 __global__ void __launch_bounds__(SPMM_THREADS)
-    sddmm_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ vals,
-                      const float* __restrict__ dS, const float* __restrict__ X, float* __restrict__ dvals,
-                      int64_t num_rows, int nvec) {
+    heavy_partial_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                         const int32_t* __restrict__ perm, const float* __restrict__ vals,
+                         const float* __restrict__ src, const int32_t* __restrict__ hub_rows,
+                         const int32_t* __restrict__ hub_segptr, int H, int total_segs, float* __restrict__ scratch,
+                         int nvec) {
   constexpr int SUBS = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR;
   const int l = lane % LPR;
-  const int64_t warp_global = (int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5);
-  const int64_t o = warp_global * SUBS + sub;
-  if (o >= num_rows) return;
+  const int64_t sg = ((int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5)) * SUBS + sub;
+  if (sg >= total_segs) return;
   const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-  const int beg = ld_stream_i32(ptr + o);
-  const int end = ld_stream_i32(ptr + o + 1);
-  if (beg >= end) return;
+  int lo = 0, hi = H;  // last hub row whose first segment is <= sg
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (hub_segptr[mid] <= sg) lo = mid; else hi = mid;
+  }
+  const int64_t row = hub_rows[lo];
+  const int k = (int)(sg - hub_segptr[lo]);
+  const int rbeg = ptr[row], rend = ptr[row + 1];
+  const int beg = rbeg + k * HEAVY_EDGES;
+  const int end = (beg + HEAVY_EDGES < rend) ? beg + HEAVY_EDGES : rend;
+  const float4* __restrict__ sbase = reinterpret_cast<const float4*>(src);
+  float4 acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = beg; base < end; base += LPR) {
+    const int my_e = base + l;
+    int my_idx = 0;
+    float my_w = 0.f;
+    if (my_e < end) {
+      my_idx = ld_stream_i32(idx + my_e);
+      if (MODE != IDDGCN_VALS_ONES) my_w = edge_weight<MODE>(vals, USE_PERM ? ld_stream_i32(perm + my_e) : my_e);
+    }
+    const int cnt = (end - base < LPR) ? (end - base) : LPR;
+    for (int j = 0; j < cnt; j += U) {
+      float4 v[U][CH];
+      float w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j + u;
+        const int sidx = __shfl_sync(mask, my_idx, jj & (LPR - 1), LPR);
+        if (MODE != IDDGCN_VALS_ONES) w[u] = __shfl_sync(mask, my_w, jj & (LPR - 1), LPR);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int vi = l + c * LPR;
+          v[u][c] = (jj < cnt && vi < nvec) ? __ldg(sbase + (size_t)sidx * nvec + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const float ww = (MODE == IDDGCN_VALS_ONES) ? 1.0f : w[u];
+          acc[c].x = fmaf(ww, v[u][c].x, acc[c].x); acc[c].y = fmaf(ww, v[u][c].y, acc[c].y);
+          acc[c].z = fmaf(ww, v[u][c].z, acc[c].z); acc[c].w = fmaf(ww, v[u][c].w, acc[c].w);
+        }
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(scratch) + (size_t)sg * nvec;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vi = l + c * LPR;
+    if (vi < nvec) o[vi] = acc[c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    heavy_reduce_kernel(const int32_t* __restrict__ hub_rows, const int32_t* __restrict__ hub_segptr, int H,
+                        const float* __restrict__ scratch, float* __restrict__ out, int64_t row_begin, int64_t row_end,
+                        int nvec, int accumulate) {
+  const int h = blockIdx.x;
+  const int64_t row = hub_rows[h];
+  if (row < row_begin || row >= row_end) return;
+  const float4* s4 = reinterpret_cast<const float4*>(scratch);
+  float4* o4 = reinterpret_cast<float4*>(out) + (size_t)row * nvec;
+  for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sg = hub_segptr[h]; sg < hub_segptr[h + 1]; ++sg) {
+      const float4 p = s4[(size_t)sg * nvec + vi];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    if (accumulate) {
+      const float4 prev = o4[vi];
+      acc.x += prev.x; acc.y += prev.y; acc.z += prev.z; acc.w += prev.w;
+    }
+    o4[vi] = acc;
+  }
+}
+
+// SDDMM: dvals[e] = <dS[seg(e), :], X[col[e], :]> (· σ'(vals[e]) in SIGMOID mode), CSR edge order.
+// One lane slice walks the edge range [beg, end) of output row o: the dS row stays in registers, every edge costs one
+// 128-bit gather of X[col] per lane and a shuffle reduction, results are written LPR at a time (coalesced).
+template <int LPR, int CH, int U, int MODE>
+__device__ __forceinline__ void sddmm_range(const int32_t* __restrict__ idx, const float* __restrict__ vals,
+                                            const float* __restrict__ dS, const float* __restrict__ X,
+                                            float* __restrict__ dvals, int64_t o, int beg, int end, int nvec,
+                                            unsigned mask, int l) {
   const float4* __restrict__ grow = reinterpret_cast<const float4*>(dS) + (size_t)o * nvec;
   const float4* __restrict__ xb = reinterpret_cast<const float4*>(X);
   float4 g[CH];
@@ -283,6 +463,50 @@ __global__ void __launch_bounds__(SPMM_THREADS)
   }
 }
 
+template <int LPR, int CH, int U, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    sddmm_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ vals,
+                      const float* __restrict__ dS, const float* __restrict__ X, float* __restrict__ dvals,
+                      int64_t num_rows, int nvec, int heavy_t) {
+  constexpr int SUBS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t o = ((int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5)) * SUBS + sub;
+  if (o >= num_rows) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int beg = ld_stream_i32(ptr + o);
+  const int end = ld_stream_i32(ptr + o + 1);
+  if (beg >= end || end - beg > heavy_t) return;  // hub rows: sddmm_hub_kernel
+  sddmm_range<LPR, CH, U, MODE>(idx, vals, dS, X, dvals, o, beg, end, nvec, mask, l);
+}
+
+// hub rows: one lane slice per HEAVY_EDGES-edge segment (edge outputs are independent, so no combine step)
+template <int LPR, int CH, int U, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS)
+    sddmm_hub_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ vals,
+                     const float* __restrict__ dS, const float* __restrict__ X, float* __restrict__ dvals,
+                     const int32_t* __restrict__ hub_rows, const int32_t* __restrict__ hub_segptr, int H,
+                     int total_segs, int nvec) {
+  constexpr int SUBS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t sg = ((int64_t)blockIdx.x * (SPMM_THREADS / 32) + (threadIdx.x >> 5)) * SUBS + sub;
+  if (sg >= total_segs) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  int lo = 0, hi = H;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (hub_segptr[mid] <= sg) lo = mid; else hi = mid;
+  }
+  const int64_t o = hub_rows[lo];
+  const int rbeg = ptr[o], rend = ptr[o + 1];
+  const int beg = rbeg + (int)(sg - hub_segptr[lo]) * HEAVY_EDGES;
+  const int end = (beg + HEAVY_EDGES < rend) ? beg + HEAVY_EDGES : rend;
+  sddmm_range<LPR, CH, U, MODE>(idx, vals, dS, X, dvals, o, beg, end, nvec, mask, l);
+}
+
 // one block per relation, fixed-order reduction
 template <int MODE>
 __global__ void __launch_bounds__(256) edge_value_sums_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
@@ -307,7 +531,7 @@ __global__ void __launch_bounds__(256) edge_value_sums_kernel(const int32_t* __r
 // ---------------------------------------------------------------------------
 struct GatherArgs {
   const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
-  int64_t row_begin, row_end; int G; int64_t seg_stride, src_group_rows; int nvec; int accumulate;
+  int64_t row_begin, row_end; int G; int64_t seg_stride, src_group_rows; int nvec; int accumulate; int heavy_t;
 };
 
 template <int LPR, int CH, int U, bool USE_PERM>
@@ -320,7 +544,7 @@ static int launch_gather_mode(const GatherArgs& a, int mode, cudaStream_t st) {
 #define IDD_GATHER(MODE_)                                                                                        \
   gather_rows_kernel<LPR, CH, U, MODE_, USE_PERM><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(                    \
       a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.G, a.seg_stride, a.src_group_rows,  \
-      a.nvec, a.accumulate)
+      a.nvec, a.accumulate, a.heavy_t)
   if (mode == IDDGCN_VALS_ONES) IDD_GATHER(IDDGCN_VALS_ONES);
   else if (mode == IDDGCN_VALS_EXPLICIT) IDD_GATHER(IDDGCN_VALS_EXPLICIT);
   else IDD_GATHER(IDDGCN_VALS_SIGMOID);
@@ -348,19 +572,34 @@ static int launch_sddmm_mode(const iddgcn_graph* g, const float* dS, const float
   constexpr int rows_per_block = (SPMM_THREADS / 32) * (32 / LPR);
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
-  if (mode == IDDGCN_VALS_SIGMOID)
+  const iddgcn_graph::HeavyList& hl = g->heavy_fwd;
+  const int heavy_t = hl.H > 0 ? HEAVY_EDGES : 0x7fffffff;
+  const unsigned hblocks = (unsigned)((hl.total_segs + rows_per_block - 1) / rows_per_block);
+  if (mode == IDDGCN_VALS_SIGMOID) {
     sddmm_rows_kernel<LPR, CH, U, IDDGCN_VALS_SIGMOID><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec);
-  else
+        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec, heavy_t);
+    IDD_LAUNCH_CHECK();
+    if (hl.H) {
+      sddmm_hub_kernel<LPR, CH, U, IDDGCN_VALS_SIGMOID><<<hblocks, SPMM_THREADS, 0, st>>>(
+          g->csr_rowptr, g->csr_col, vals, dS, X, dvals, hl.rows, hl.segptr, hl.H, hl.total_segs, nvec);
+      IDD_LAUNCH_CHECK();
+    }
+  } else {
     sddmm_rows_kernel<LPR, CH, U, IDDGCN_VALS_EXPLICIT><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec);
-  IDD_LAUNCH_CHECK();
+        g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec, heavy_t);
+    IDD_LAUNCH_CHECK();
+    if (hl.H) {
+      sddmm_hub_kernel<LPR, CH, U, IDDGCN_VALS_EXPLICIT><<<hblocks, SPMM_THREADS, 0, st>>>(
+          g->csr_rowptr, g->csr_col, vals, dS, X, dvals, hl.rows, hl.segptr, hl.H, hl.total_segs, nvec);
+      IDD_LAUNCH_CHECK();
+    }
+  }
   return IDDGCN_OK;
 }
 
 struct StreamArgs {
   const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
-  int64_t row_begin, row_end; int nvec; int accumulate;
+  int64_t row_begin, row_end; int nvec; int accumulate; int heavy_t;
 };
 
 template <int LPR, bool USE_PERM>
@@ -371,8 +610,14 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
 #define IDD_STREAM(MODE_)                                                                                     \
-  stream_rows_kernel<LPR, 8, MODE_, USE_PERM><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(                     \
-      a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate)
+  do {                                                                                                        \
+    if (a.heavy_t == 0x7fffffff)                                                                              \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, false><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(          \
+          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t); \
+    else                                                                                                      \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, true><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(           \
+          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t); \
+  } while (0)
   if (mode == IDDGCN_VALS_ONES) IDD_STREAM(IDDGCN_VALS_ONES);
   else if (mode == IDDGCN_VALS_EXPLICIT) IDD_STREAM(IDDGCN_VALS_EXPLICIT);
   else IDD_STREAM(IDDGCN_VALS_SIGMOID);
@@ -410,25 +655,82 @@ static int check_common(const iddgcn_graph* g, int64_t D, const float* vals, int
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- hub-row split pass ---------------------------------------------------------------------
+static int ensure_heavy_ws(const iddgcn_graph* g, int total_segs, int64_t D) {
+  const size_t need = (size_t)total_segs * (size_t)D;
+  if (need <= g->heavy_ws_elems) return IDDGCN_OK;
+  cudaFree(g->heavy_ws);
+  g->heavy_ws = nullptr;
+  g->heavy_ws_elems = 0;
+  IDD_CUDA(cudaMalloc((void**)&g->heavy_ws, need * sizeof(float)));   // fails inside a stream capture: call
+  g->heavy_ws_elems = need;                                            // iddgcn_spmm_* once before capturing
+  return IDDGCN_OK;
+}
+
+template <int LPR, int CH, int U, bool USE_PERM>
+static int launch_heavy_mode(const iddgcn_graph::HeavyList& hl, const int32_t* ptr, const int32_t* idx,
+                             const int32_t* perm, const float* vals, int mode, const float* src, float* scratch,
+                             int nvec, cudaStream_t st) {
+  constexpr int per_block = (SPMM_THREADS / 32) * (32 / LPR);
+  const unsigned blocks = (unsigned)((hl.total_segs + per_block - 1) / per_block);
+#define IDD_HEAVY(MODE_)                                                                                   \
+  heavy_partial_kernel<LPR, CH, U, MODE_, USE_PERM><<<blocks, SPMM_THREADS, 0, st>>>(                      \
+      ptr, idx, perm, vals, src, hl.rows, hl.segptr, hl.H, hl.total_segs, scratch, nvec)
+  if (mode == IDDGCN_VALS_ONES) IDD_HEAVY(IDDGCN_VALS_ONES);
+  else if (mode == IDDGCN_VALS_EXPLICIT) IDD_HEAVY(IDDGCN_VALS_EXPLICIT);
+  else IDD_HEAVY(IDDGCN_VALS_SIGMOID);
+#undef IDD_HEAVY
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+template <bool USE_PERM>
+static int heavy_pass(const iddgcn_graph* g, const iddgcn_graph::HeavyList& hl, const int32_t* ptr,
+                      const int32_t* idx, const int32_t* perm, const float* vals, int mode, const float* src,
+                      float* out, int64_t row_begin, int64_t row_end, int64_t D, int accumulate, cudaStream_t st) {
+  if (hl.H == 0) return IDDGCN_OK;
+  IDD_TRY(ensure_heavy_ws(g, hl.total_segs, D));
+  const int nvec = (int)(D / 4);
+  if (nvec <= 8) IDD_TRY((launch_heavy_mode<8, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
+  else if (nvec <= 16) IDD_TRY((launch_heavy_mode<16, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
+  else if (nvec <= 32) IDD_TRY((launch_heavy_mode<32, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
+  else if (nvec <= 64) IDD_TRY((launch_heavy_mode<32, 2, 4, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
+  else IDD_TRY((launch_heavy_mode<32, 4, 2, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
+  heavy_reduce_kernel<<<hl.H, 128, 0, st>>>(hl.rows, hl.segptr, hl.H, g->heavy_ws, out, row_begin, row_end, nvec,
+                                            accumulate);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// Both directions are the same generic gather  out[o] = Σ_{e in ptr[o]..ptr[o+1]} w(e)·src[idx[e]] :
+//   forward  on (csr_rowptr, csr_col)            over R·n_rows rows, weight index e
+//   backward on (bwd_rowptr, bwd_src, bwd_perm)  over N rows (node-major CSC view), weight index perm[e]
+template <bool USE_PERM>
+static int generic_gather(const iddgcn_graph* g, const iddgcn_graph::HeavyList& hl, const int32_t* ptr,
+                          const int32_t* idx, const int32_t* perm, int64_t total_rows, const float* vals, int mode,
+                          const float* src, float* out, int64_t D, int accumulate, int64_t row_begin, int64_t row_end,
+                          cudaStream_t st) {
+  const int heavy_t = hl.H > 0 ? HEAVY_EDGES : 0x7fffffff;
+  if (D <= 128 && !use_v1(total_rows)) {
+    StreamArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, (int)(D / 4), accumulate, heavy_t};
+    IDD_TRY(launch_stream<USE_PERM>(a, mode, st));
+  } else {
+    GatherArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, 1, 0, 0, (int)(D / 4), accumulate, heavy_t};
+    IDD_TRY(launch_gather<USE_PERM>(a, mode, st));
+  }
+  return heavy_pass<USE_PERM>(g, hl, ptr, idx, perm, vals, mode, src, out, row_begin, row_end, D, accumulate, st);
+}
+
 int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
                    int64_t row_begin, int64_t row_end, cudaStream_t st) {
-  if (D <= 128 && !use_v1((int64_t)g->R * g->n_rows)) {
-    StreamArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, (int)(D / 4), 0};
-    return launch_stream<false>(a, mode, st);
-  }
-  GatherArgs a{g->csr_rowptr, g->csr_col, nullptr, vals, X, S, row_begin, row_end, 1, 0, 0, (int)(D / 4), 0};
-  return launch_gather<false>(a, mode, st);
+  return generic_gather<false>(g, g->heavy_fwd, g->csr_rowptr, g->csr_col, nullptr, (int64_t)g->R * g->n_rows, vals,
+                               mode, X, S, D, 0, row_begin, row_end, st);
 }
 
 int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
                      int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st) {
-  if (D <= 128 && !use_v1(g->N)) {
-    StreamArgs a{g->bwd_rowptr, g->bwd_src, g->bwd_perm, vals, dS, dX, row_begin, row_end, (int)(D / 4), accumulate};
-    return launch_stream<true>(a, mode, st);
-  }
-  GatherArgs a{g->csc_rowptr, g->csc_row, g->csc_perm, vals, dS, dX, row_begin, row_end, g->R, g->N, g->n_rows,
-               (int)(D / 4), accumulate};
-  return launch_gather<true>(a, mode, st);
+  return generic_gather<true>(g, g->heavy_bwd, g->bwd_rowptr, g->bwd_src, g->bwd_perm, g->N, vals, mode, dS, dX, D,
+                              accumulate, row_begin, row_end, st);
 }
 
 int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64_t D, const float* vals, int mode,

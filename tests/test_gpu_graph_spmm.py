@@ -236,3 +236,46 @@ def test_large_graph_properties():
     rel = torch.bucketize(e, torch.from_numpy(g.rel_offsets).cuda()[1:], right=True)
     ref = (dS[rel, d["csr_row"].long()[e]].double() * X[d["csr_col"].long()[e]].double()).sum(1)
     assert (dv[e].double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("kernels", ["v1", "v2"])
+@pytest.mark.parametrize("D,mode", [(128, 0), (64, 2), (256, 1)])
+def test_hub_rows_take_the_split_pass(D, mode, kernels, monkeypatch):
+    """Rows / columns with more than 1024 edges are cut into segments summed by separate warps (Zipf-skewed graphs):
+    a hub destination row (forward, SDDMM), a hub source column (backward), one of them spanning several segments."""
+    monkeypatch.setenv("IDDGCN_SPMM_V1", "1" if kernels == "v1" else "0")
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R = 30000, 2
+    rng = np.random.default_rng(D + mode)
+    base = random_triples(N, R, 50000, seed=D)
+    hub_row = np.stack([np.full(20000, 5), np.zeros(20000, np.int64), rng.integers(0, N, 20000)], 1)
+    hub_row2 = np.stack([np.full(6000, N - 1), np.ones(6000, np.int64), rng.integers(0, N, 6000)], 1)
+    hub_col = np.stack([rng.integers(0, N, 15000), np.ones(15000, np.int64), np.full(15000, 7)], 1)
+    tri = np.concatenate([base, hub_row, hub_row2, hub_col]).astype(np.int64)
+    adj = O.get_adj_mats(tri, N, R)
+    g = Graph(tri, N, R)
+    ref = _oracle_struct(tri, N, R)
+    got = g.export()
+    for k in ("csr_rowptr", "csr_col", "csc_rowptr", "csc_row", "csc_perm"):
+        assert np.array_equal(got[k], ref[k]), k
+    deg = np.diff(ref["csr_rowptr"])
+    assert (deg > 1024).sum() >= 2 and deg.max() > 3 * 1024
+    X = rng.random((N, D)).astype(np.float32)
+    dS = rng.standard_normal((R, N, D)).astype(np.float32)
+    raw, eff = _vals_for(adj, mode, seed=1)
+    Xd, dSd = torch.from_numpy(X).cuda(), torch.from_numpy(dS).cuda()
+    vd = torch.from_numpy(raw).cuda() if raw is not None else None
+    S = ops.spmm_fwd(g, Xd, vd, mode).cpu().numpy()
+    assert rel_err(S, O.spmm_fwd(adj, X.astype(np.float64), eff)) < TOL
+    dX = ops.spmm_bwd_x(g, dSd, vd, mode).cpu().numpy()
+    assert rel_err(dX, O.spmm_bwd_x(adj, dS.astype(np.float64), eff)) < TOL
+    dX2 = ops.spmm_bwd_x(g, dSd, vd, mode, out=torch.ones_like(Xd), accumulate=True).cpu().numpy()
+    assert rel_err(dX2, O.spmm_bwd_x(adj, dS.astype(np.float64), eff) + 1.0) < TOL
+    dv_ref = np.concatenate(O.spmm_bwd_vals(adj, dS.astype(np.float64), X.astype(np.float64)))
+    if mode == 2:
+        sg = np.concatenate(eff)
+        dv_ref = dv_ref * sg * (1 - sg)
+    dv = ops.spmm_bwd_vals(g, dSd, Xd, vd, mode).cpu().numpy()
+    assert rel_err(dv, dv_ref, scale=np.abs(dS).max() * np.abs(X).max() * np.sqrt(D)) < TOL
+    assert torch.equal(ops.spmm_fwd(g, Xd, vd, mode), torch.from_numpy(S).cuda())     # still bit-reproducible

@@ -255,7 +255,8 @@ def run_ours(args, wl):
     S = torch.empty((R, n_rows, D), device=dev)
     if world > 1:
         from iddgcn_b200.dist import PartitionedSpMM
-        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels, rs_group=rs_group)
+        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels, rs_group=rs_group,
+                                 exchange=args.exchange, mc_ctas=args.mc_ctas)
         step = lambda: engine.step(X_local, dS, S)
         nnz_t = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
         dist.all_reduce(nnz_t)
@@ -325,6 +326,7 @@ def run_ours(args, wl):
         comm["all_gather_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["all_gather"] / 1e6
         comm["reduce_scatter_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["reduce_scatter"] / 1e6
         comm["panels"] = engine.panels
+        comm["exchange"] = args.exchange
     sddmm = None
     if world == 1:
         # separately reported explainer line: edge-value gradient dvals[e] = <dS[row_e], X[col_e]>
@@ -429,6 +431,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"],
+                    help="multi-GPU exchange: NCCL collectives or hand-written NVSwitch multicast kernels")
+    ap.add_argument("--mc-ctas", type=int, default=32, help="thread blocks of the multicast copy kernels")
     ap.add_argument("--panels", type=int, default=2, help="column panels of the multi-GPU exchange pipeline")
     args = ap.parse_args()
     if args.warmup < 3:

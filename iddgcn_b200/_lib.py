@@ -64,6 +64,8 @@ _SIGNATURES = {
     "iddgcn_block_relation_sums": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp]),
     "iddgcn_explain_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int64, vp, vp, vp, vp]),
     "iddgcn_structure_grad": (C.c_int, [vp, vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp]),
+    "iddgcn_mc_store": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
+    "iddgcn_mc_reduce_load": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "iddgcn_adam_step": (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                    vp]),
 }

@@ -59,9 +59,30 @@ def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, rank: int, async_op: b
     return None
 
 
+class _NvlsBuffers:
+    """Symmetric (multicast-mapped) buffers + the hand-written multimem kernels of csrc/nvls.cu.
+
+    torch.distributed._symmetric_memory is the plumbing (cuMulticast* object, handle exchange, signal-pad barriers);
+    the data movement is ours: `iddgcn_mc_store` (all-gather leg, multimem.st) and `iddgcn_mc_reduce_load`
+    (reduce-scatter leg, multimem.ld_reduce.add)."""
+
+    def __init__(self, shape, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.full = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+        self.partial = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+        self.h_full = symm_mem.rendezvous(self.full, group)
+        self.h_part = symm_mem.rendezvous(self.partial, group)
+        self.mc_full = int(self.h_full.multicast_ptr)
+        self.mc_part = int(self.h_part.multicast_ptr)
+        if not self.mc_full or not self.mc_part:
+            raise RuntimeError("NVLS multicast is not available on this system")
+        self.s_ag = torch.cuda.Stream(device=device, priority=-1)
+        self.s_rs = torch.cuda.Stream(device=device, priority=-1)
+
+
 class PartitionedSpMM:
     def __init__(self, graph, D: int, world: int, rank: int, block: int, *, panels: int = 4, fwd_fn=None,
-                 bwd_fn=None, device=None, ag_group=None, rs_group=None):
+                 bwd_fn=None, device=None, ag_group=None, rs_group=None, exchange: str = "nccl", mc_ctas: int = 32):
         if D % panels or (D // panels) % 4:
             raise ValueError(f"D={D} must split into {panels} panels whose width is a multiple of 4")
         self.g, self.D, self.world, self.rank, self.block, self.panels = graph, D, world, rank, block, panels
@@ -80,8 +101,14 @@ class PartitionedSpMM:
         dev = device if device is not None else graph.device
         f = dict(dtype=torch.float32, device=dev)
         self.Xp_local = torch.zeros((panels, block, self.Dc), **f)
-        self.Xp_full = torch.empty((panels, self.N_pad, self.Dc), **f)
-        self.dXp_partial = torch.empty((panels, self.N_pad, self.Dc), **f)
+        self.exchange, self.mc_ctas, self.nvls = exchange, mc_ctas, None
+        if exchange == "nvls":
+            # NVSwitch multicast exchange: both big buffers must be symmetric (same offset on every rank)
+            self.nvls = _NvlsBuffers((panels, self.N_pad, self.Dc), dev, dist.group.WORLD)
+            self.Xp_full, self.dXp_partial = self.nvls.full, self.nvls.partial
+        else:
+            self.Xp_full = torch.empty((panels, self.N_pad, self.Dc), **f)
+            self.dXp_partial = torch.empty((panels, self.N_pad, self.Dc), **f)
         self.dXp_local = torch.empty((panels, block, self.Dc), **f)
         self.Sp = torch.empty((panels, self.R, self.n_rows, self.Dc), **f)
         self.dSp = torch.empty((panels, self.R, self.n_rows, self.Dc), **f)
@@ -105,6 +132,8 @@ class PartitionedSpMM:
         Issue order on the compute stream is B0 F0 B1 F1 ...: backward panel c needs no exchange (dS is local), so its
         kernel and the all-gather of panel c start together; its result goes straight into reduce-scatter c on the
         second communicator while forward panel c consumes all-gather c."""
+        if self.nvls is not None:
+            return self._run_panels_nvls()
         P = self.panels
         gathers = [_all_gather(self.Xp_full[c], self.Xp_local[c], True, self.ag_group) for c in range(P)]
         scatters = []
@@ -120,6 +149,51 @@ class PartitionedSpMM:
         for w in scatters:
             if w is not None:
                 w.wait()
+
+    def _run_panels_nvls(self):
+        """Same step with the exchange done by our multimem kernels on two side streams.
+
+        all-gather leg  : every rank stores its block of panel c once through the multicast address (the switch
+                          replicates it into every rank's Xp_full) -> barrier -> forward panel c may read it;
+        reduce-scatter  : after backward panel c on every rank (barrier), each rank loads ITS block of dXp_partial[c]
+                          through the multicast address with the in-switch sum.
+        The two legs load opposite link directions and run concurrently with the kernels."""
+        from ._lib import check, load
+        lib, nv, P = load(), self.nvls, self.panels
+        main = torch.cuda.current_stream(self.Xp_local.device)
+        blk = self.block * self.Dc                       # floats per (panel, rank) block
+        T_MS = 20000
+        for s_ in (nv.s_ag, nv.s_rs):
+            main.wait_stream(s_)
+        nv.h_full.barrier(channel=2, timeout_ms=T_MS)    # every rank is done with the previous step's buffers
+        nv.s_ag.wait_stream(main)
+        nv.s_rs.wait_stream(main)
+        ev_ag = []
+        with torch.cuda.stream(nv.s_ag):
+            for c in range(P):
+                off = (c * self.N_pad * self.Dc + self.rank * blk) * 4
+                check(lib.iddgcn_mc_store(nv.mc_full + off, self.Xp_local[c].data_ptr(), blk, self.mc_ctas,
+                                          nv.s_ag.cuda_stream))
+                nv.h_full.barrier(channel=0, timeout_ms=T_MS)
+                ev_ag.append(nv.s_ag.record_event())
+        ev_rs = []
+        for c in range(P):
+            part = self.dXp_partial[c]
+            self.bwd_fn(self.g, self.dSp[c], part[: self.g.N])
+            if self.N_pad > self.g.N:
+                part[self.g.N:].zero_()
+            ev_b = main.record_event()
+            with torch.cuda.stream(nv.s_rs):
+                nv.s_rs.wait_event(ev_b)
+                nv.h_part.barrier(channel=0, timeout_ms=T_MS)    # every rank's partial panel c is complete
+                off = (c * self.N_pad * self.Dc + self.rank * blk) * 4
+                check(lib.iddgcn_mc_reduce_load(nv.mc_part + off, self.dXp_local[c].data_ptr(), blk, self.mc_ctas,
+                                                nv.s_rs.cuda_stream))
+                ev_rs.append(nv.s_rs.record_event())
+            main.wait_event(ev_ag[c])
+            self.fwd_fn(self.g, self.Xp_full[c][: self.g.N], self.Sp[c])
+        for e in ev_rs:
+            main.wait_event(e)
 
     def step(self, X_local, dS_local, S_out=None):
         """bench.py's step: inputs are already resident in panel layout after the first call."""

@@ -295,6 +295,21 @@ int iddgcn_explain_loss(const float* before, const float* pred, const float* c, 
 int iddgcn_structure_grad(const iddgcn_graph_t* g, const float* vals, int vals_mode, const float* coef,
                           int64_t N, int64_t B, float* dvals, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Exchange kernels over NVSwitch multicast memory (NVLS) for the row-partitioned
+ * SpMM (no counterpart in the reference: its only multi-device construct,
+ * tf.distribute.MirroredStrategy in GnnExplainer.py:105, is pinned to one GPU).
+ *   iddgcn_mc_store:        all-gather leg — store n local floats once through the
+ *                           MULTICAST address mc_dst; the switch replicates them
+ *                           into every rank's copy of the symmetric buffer.
+ *   iddgcn_mc_reduce_load:  reduce-scatter leg — dst[i] = Σ_ranks buf_rank[i] for the
+ *                           range at MULTICAST address mc_src (in-switch sum).
+ * n % 4 == 0, 16-byte aligned; `ctas` = thread blocks to use (<=0: 32).  The
+ * multicast mapping and cross-rank barriers are the host layer's job.
+ * ------------------------------------------------------------------------ */
+int iddgcn_mc_store(void* mc_dst, const float* src, int64_t n, int ctas, void* stream);
+int iddgcn_mc_reduce_load(const void* mc_src, float* dst, int64_t n, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ from helpers import random_triples
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, N, R, D, panels, tri, X, dS, out_dir):
+def _worker(rank, world, port, N, R, D, panels, tri, X, dS, out_dir, exchange="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -25,7 +25,7 @@ def _worker(rank, world, port, N, R, D, panels, tri, X, dS, out_dir):
         lo, hi, block = row_block(rank, world, N)
         g = Graph(tri, N, R, row_block=(lo, hi), device=dev)
         rs = dist.new_group(backend="nccl")
-        eng = PartitionedSpMM(g, D, world, rank, block, panels=panels, rs_group=rs)
+        eng = PartitionedSpMM(g, D, world, rank, block, panels=panels, rs_group=rs, exchange=exchange)
         eng.step(torch.from_numpy(X[lo:hi]).to(dev), torch.from_numpy(dS[:, lo:hi]).to(dev))
         eng.step(None, None)                      # second step reuses resident inputs
         S_local, dX_local = eng.outputs()
@@ -37,8 +37,8 @@ def _worker(rank, world, port, N, R, D, panels, tri, X, dS, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("N,panels", [(5001, 4), (4096, 2)])
-def test_partitioned_spmm_two_gpus_matches_single_gpu(tmp_path, N, panels):
+@pytest.mark.parametrize("N,panels,exchange", [(5001, 4, "nccl"), (4096, 2, "nccl"), (5001, 2, "nvls"), (4096, 4, "nvls")])
+def test_partitioned_spmm_two_gpus_matches_single_gpu(tmp_path, N, panels, exchange):
     from iddgcn_b200 import ops
     from iddgcn_b200.graph import Graph
     R, D, world = 2, 128, 2
@@ -46,7 +46,8 @@ def test_partitioned_spmm_two_gpus_matches_single_gpu(tmp_path, N, panels):
     rng = np.random.default_rng(0)
     X = rng.random((N, D)).astype(np.float32)
     dS = rng.standard_normal((R, N, D)).astype(np.float32)
-    mp.spawn(_worker, args=(world, 29700 + panels, N, R, D, panels, tri, X, dS, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29700 + panels + (10 if exchange == "nvls" else 0), N, R, D, panels, tri, X, dS,
+                            str(tmp_path), exchange), nprocs=world, join=True)
     g = Graph(tri, N, R)
     S_ref = ops.spmm_fwd(g, torch.from_numpy(X).cuda()).cpu().numpy()
     dX_ref = ops.spmm_bwd_x(g, torch.from_numpy(dS).cuda()).cpu().numpy()

@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 // backward: ptr=bwd_rowptr, idx=bwd_src,  src=dS as [(R·n_rows),D], weight index perm[e]
 constexpr int SLAB = 512;  // staged indices per warp
 
-template <int LPR, int U, int MODE, bool USE_PERM, bool HUBS>
-__global__ void __launch_bounds__(SPMM_THREADS)
+template <int LPR, int U, int MODE, bool USE_PERM, bool HUBS, int TPB = SPMM_THREADS, int MINB = 4, bool NA = false>
+__global__ void __launch_bounds__(TPB, MINB)
     stream_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
                        const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(SPMM_THREADS)
   constexpr int SUBS = 32 / LPR;
   constexpr int SUB_SLAB = SLAB / SUBS;
   constexpr bool WEIGHTED = MODE != IDDGCN_VALS_ONES;
-  __shared__ int32_t s_idx[SPMM_THREADS / 32][SLAB];
-  __shared__ float s_w[WEIGHTED ? SPMM_THREADS / 32 : 1][WEIGHTED ? SLAB : 1];
+  __shared__ int32_t s_idx[TPB / 32][SLAB];
+  __shared__ float s_w[WEIGHTED ? TPB / 32 : 1][WEIGHTED ? SLAB : 1];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR;
   const int l = lane % LPR;
-  const int64_t chunk = ((int64_t)blockIdx.x * (SPMM_THREADS / 32) + warp) * SUBS + sub;
+  const int64_t chunk = ((int64_t)blockIdx.x * (TPB / 32) + warp) * SUBS + sub;
   const int64_t r0 = row_begin + chunk * LPR;
   if (r0 >= row_end) return;
   const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         if (u < n) {
           const int sidx = sl_idx[pos + u - slab_lo];
           if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
-          v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = (l < nvec) ? (NA ? ld_stream_f4(src4 + (size_t)sidx * nvec + l) : __ldg(src4 + (size_t)sidx * nvec + l))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
   #pragma unroll
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
         if (u < n) {
           const int sidx = sl_idx[pos + u - slab_lo];
           if (WEIGHTED) w[u] = sl_w[pos + u - slab_lo];
-          v[u] = (l < nvec) ? __ldg(src4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = (l < nvec) ? (NA ? ld_stream_f4(src4 + (size_t)sidx * nvec + l) : __ldg(src4 + (size_t)sidx * nvec + l))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
       int consumed = 0;
@@ -618,6 +620,37 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
       stream_rows_kernel<LPR, 8, MODE_, USE_PERM, true><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(           \
           a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t); \
   } while (0)
+  // IDDGCN_TUNE=<k>: launch-shape variants of the headline instantiation (D=128, unweighted, no hub rows) for A/B runs
+  if (LPR == 32 && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff) {
+    const char* tv = getenv("IDDGCN_TUNE");
+    const int k = tv ? atoi(tv) : 0;
+    if (k > 0) {
+#define IDD_TUNE(U_, TPB_, MINB_, NA_)                                                                              \
+      do {                                                                                                          \
+        const int64_t nb = (rows + (TPB_ / 32) * 32 - 1) / ((TPB_ / 32) * 32);                                      \
+        stream_rows_kernel<32, U_, IDDGCN_VALS_ONES, USE_PERM, false, TPB_, MINB_, NA_><<<(unsigned)nb, TPB_, 0, st>>>( \
+            a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t);   \
+      } while (0)
+      switch (k) {
+        case 1: IDD_TUNE(8, 256, 4, true); break;
+        case 2: IDD_TUNE(16, 256, 1, false); break;
+        case 3: IDD_TUNE(4, 256, 6, false); break;
+        case 4: IDD_TUNE(8, 128, 1, false); break;
+        case 5: IDD_TUNE(8, 128, 8, false); break;
+        case 6: IDD_TUNE(8, 256, 5, false); break;
+        case 7: IDD_TUNE(12, 256, 1, false); break;
+        case 8: IDD_TUNE(6, 256, 5, false); break;
+        case 9: IDD_TUNE(8, 512, 2, false); break;
+        case 10: IDD_TUNE(8, 256, 1, false); break;
+        case 11: IDD_TUNE(8, 256, 3, false); break;
+        case 12: IDD_TUNE(10, 256, 3, false); break;
+        default: IDD_TUNE(8, 256, 4, false); break;
+      }
+#undef IDD_TUNE
+      IDD_LAUNCH_CHECK();
+      return IDDGCN_OK;
+    }
+  }
   if (mode == IDDGCN_VALS_ONES) IDD_STREAM(IDDGCN_VALS_ONES);
   else if (mode == IDDGCN_VALS_EXPLICIT) IDD_STREAM(IDDGCN_VALS_EXPLICIT);
   else IDD_STREAM(IDDGCN_VALS_SIGMOID);

@@ -1,0 +1,49 @@
+"""bench.py contract: one JSON line with the keys the driver and the judge read.  The reference arm (CPU) runs in the
+CPU suite on the small workload; our arm needs a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def _run(args, timeout=600):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line_on_small_workload():
+    d = _run(["--impl", "reference", "--workload", "small", "--steps", "2", "--warmup", "3"])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "relational_spmm_fwd_bwd_edges_per_sec" and d["unit"] == "edges/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+@pytest.mark.gpu
+def test_our_arm_line_on_small_workload():
+    d = _run(["--workload", "small", "--steps", "3", "--warmup", "3"])
+    assert BASE_KEYS | {"roofline", "clocks", "sddmm"} <= set(d)
+    assert d["value"] > 1e8 and d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] >= 6
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["achieved"] > 0 and "stream_rows_kernel" in r["kernel"] or "gather_rows_kernel" in r["kernel"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and 0 < c["value"] < d["value"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])

@@ -195,6 +195,7 @@ def test_large_graph_properties():
     from iddgcn_b200 import ops
     from iddgcn_b200.graph import Graph
     N, R, D, per_rel = 1_000_000, 2, 128, 10_000_000
+    torch.manual_seed(0)
     gen = torch.Generator(device="cuda").manual_seed(0)
     h = torch.randint(0, N, (R * per_rel,), device="cuda", generator=gen)
     t = torch.randint(0, N, (R * per_rel,), device="cuda", generator=gen)
@@ -228,10 +229,13 @@ def test_large_graph_properties():
     dX = ops.spmm_bwd_x(g, dS)
     lhs = (S.double() * dS.double()).sum().item()
     rhs = (X.double() * dX.double()).sum().item()
-    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+    # both sides are sums of 2.6e8 random-sign terms computed from fp32 S / dX: the rounding noise of such a sum is
+    # ~1e-7·sqrt(numel)·rms(S)·rms(dS) (~0.01 here) while a structural error (e.g. a transposition) is ~sqrt(numel)·rms
+    noise = 1e-7 * (S.numel() ** 0.5) * S.double().pow(2).mean().sqrt().item() * dS.double().pow(2).mean().sqrt().item()
+    assert abs(lhs - rhs) <= 50 * noise, (lhs, rhs, noise)
     # SDDMM at full size: Σ_e dvals[e] = <A·X, dS> (values all 1), and a sample of edges against direct dot products
     dv = ops.spmm_bwd_vals(g, dS, X)
-    assert abs(dv.double().sum().item() - lhs) <= 1e-6 * max(abs(lhs), 1.0)
+    assert abs(dv.double().sum().item() - lhs) <= 50 * noise
     e = torch.randint(0, g.nnz, (100000,), device="cuda")
     rel = torch.bucketize(e, torch.from_numpy(g.rel_offsets).cuda()[1:], right=True)
     ref = (dS[rel, d["csr_row"].long()[e]].double() * X[d["csr_col"].long()[e]].double()).sum(1)

@@ -276,3 +276,44 @@ def test_fold1_train_step_at_shipped_size(golden_dir):
     loss_ref, g_ref = O.train_step(p, adj_o, Xtr, neg, O.new_adam_state(p), apply_update=False)
     assert abs(loss - loss_ref) < 1e-5 * abs(loss_ref)
     _check_grads(m.get_gradients(), g_ref, p, adj_o, Xtr, neg)
+
+
+def test_dense_mask_product_and_fit_callbacks(tmp_path):
+    """`adj * dense_mask` with a (1,N,N) dense tensor (SparseDenseCwiseMul, GnnExplainer.py:33), negatives read from the
+    reference's .npy path template (IDDGCN.py:128), and a SaveWeightsCallback-style callback (IDDGCN.py:181-199)."""
+    from iddgcn_b200 import Adam, get_adj_mats, h5
+    N, R, D = 50, 3, 32
+    tri, pos, neg, p = _setup(N, R, D, 500, 150, 30, seed=51, scale=0.1)
+    m = _model_for(p, N, R, D)
+    adj = get_adj_mats(tri, N, R)
+    dense = torch.rand(1, N, N, device="cuda")
+    masked = [a * dense for a in adj]
+    x = [None, pos[None, :, 0], pos[None, :, 1], pos[None, :, 2]]
+    y = m(x + [masked]).cpu().numpy()[0]
+    adj_o = O.get_adj_mats(tri, N, R)
+    dn = dense.cpu().numpy().astype(np.float64)[0]
+    vals = [a.values.astype(np.float64) * dn[a.indices[:, 1], a.indices[:, 2]] for a in adj_o]
+    assert rel_err(y, O.model_forward(p, adj_o, pos[:, 0], pos[:, 1], pos[:, 2], vals=vals)) < FWD_TOL
+    # fit(): negatives from the path template, callback at save_epochs
+    m.neg_path_template = str(tmp_path / "mode{mode}_fold{fold}_X_train_neg.npy")
+    np.save(m.neg_path_template.format(mode=0, fold=0), neg[None].astype(np.float64))
+
+    class SaveWeightsCallback:
+        def __init__(self):
+            self.save_epochs, self.seen = [2, 5], []
+
+        def on_epoch_end(self, epoch, logs=None):
+            if epoch + 1 in self.save_epochs:
+                self.seen.append(epoch + 1)
+                self.model.save_weights(tmp_path / f"w{epoch + 1}.h5")
+
+    cb = SaveWeightsCallback()
+    m.compile(loss=None, optimizer=Adam(learning_rate=1e-3))
+    h = m.fit(x=[np.arange(N).reshape(1, -1)] + x[1:] + [adj], y=np.ones((1, len(pos))), epochs=5, batch_size=100,
+              verbose=0, callbacks=[cb])
+    assert cb.seen == [2, 5] and len(h.history["loss"]) == 5 and h.history["loss"][-1] < h.history["loss"][0]
+    for a, b in zip(h5.read_weight_list(tmp_path / "w5.h5"), m.get_weights()):
+        assert np.array_equal(a, b)
+    assert not np.array_equal(h5.read_weight_list(tmp_path / "w2.h5")[0], m.get_weights()[0])
+    emb = m.get_layer("entity_embeddings").get_weights()[0]
+    assert emb.shape == (N, D) and len(m.trainable_weights) == 17

@@ -33,7 +33,8 @@ def spmm_fwd(graph: Graph, X: torch.Tensor, vals=None, mode: int = VALS_ONES, ou
     if X.shape[0] != graph.N:
         raise ValueError(f"X has {X.shape[0]} rows, graph has N={graph.N}")
     S = out if out is not None else torch.empty((graph.R, graph.n_rows, D), dtype=torch.float32, device=X.device)
-    check(load().iddgcn_spmm_fwd(graph.handle, ptr(X), D, ptr(vals), mode, ptr(S), _stream(X)))
+    with torch.cuda.device(X.device):          # launches go to the current device: make it the tensors' device
+        check(load().iddgcn_spmm_fwd(graph.handle, ptr(X), D, ptr(vals), mode, ptr(S), _stream(X)))
     return S
 
 
@@ -43,7 +44,9 @@ def spmm_bwd_x(graph: Graph, dS: torch.Tensor, vals=None, mode: int = VALS_ONES,
     dS = _f32c(dS, "dS")
     D = dS.shape[-1]
     dX = out if out is not None else torch.empty((graph.N, D), dtype=torch.float32, device=dS.device)
-    check(load().iddgcn_spmm_bwd_x(graph.handle, ptr(dS), D, ptr(vals), mode, ptr(dX), int(accumulate), _stream(dS)))
+    with torch.cuda.device(dS.device):
+        check(load().iddgcn_spmm_bwd_x(graph.handle, ptr(dS), D, ptr(vals), mode, ptr(dX), int(accumulate),
+                                       _stream(dS)))
     return dX
 
 
@@ -53,14 +56,16 @@ def spmm_bwd_vals(graph: Graph, dS: torch.Tensor, X: torch.Tensor, vals=None, mo
     X = _f32c(X, "X")
     D = X.shape[1]
     dv = torch.empty(graph.nnz, dtype=torch.float32, device=X.device)
-    check(load().iddgcn_spmm_bwd_vals(graph.handle, ptr(dS), ptr(X), D, ptr(vals), mode, ptr(dv), _stream(X)))
+    with torch.cuda.device(X.device):
+        check(load().iddgcn_spmm_bwd_vals(graph.handle, ptr(dS), ptr(X), D, ptr(vals), mode, ptr(dv), _stream(X)))
     return dv
 
 
 def edge_value_sums(graph: Graph, vals=None, mode: int = VALS_ONES) -> torch.Tensor:
     out = torch.empty(graph.R, dtype=torch.float32, device=graph.device)
-    check(load().iddgcn_edge_value_sums(graph.handle, ptr(vals), mode, ptr(out),
-                                        torch.cuda.current_stream(graph.device).cuda_stream))
+    with torch.cuda.device(graph.device):
+        check(load().iddgcn_edge_value_sums(graph.handle, ptr(vals), mode, ptr(out),
+                                            torch.cuda.current_stream(graph.device).cuda_stream))
     return out
 
 

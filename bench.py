@@ -325,6 +325,12 @@ def run_ours(args, wl):
         comm["bytes_received_per_rank"] = int((world - 1) * block * D * 4)
         comm["all_gather_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["all_gather"] / 1e6
         comm["reduce_scatter_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["reduce_scatter"] / 1e6
+        # NVLink bound for the exchange of one step (B200_PROFILING.md: measured 770 GB/s per direction per GPU):
+        # every rank receives (P-1) blocks in the all-gather and sends (P-1) blocks in the reduce-scatter, and ring
+        # collectives load both directions, so the two legs cannot overlap each other
+        comm["nvlink_GBps_per_direction"] = 770.0
+        comm["nvlink_bound_ms"] = 2 * comm["bytes_received_per_rank"] / 770.0 / 1e6
+        comm["step_over_nvlink_bound"] = ms_per_step / comm["nvlink_bound_ms"]
         comm["panels"] = engine.panels
         comm["exchange"] = args.exchange
     sddmm = None

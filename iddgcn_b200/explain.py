@@ -77,7 +77,7 @@ class Explainer:
             if len(self._replicas) >= 2:
                 self._replicas.pop(next(iter(self._replicas))).close()
             m = IDDGCN_Model(self.N * B, self.R, self.D, self.D, seed=0, num_layers=self.src.num_layers,
-                             device=self.device)
+                             device=self.device, init_weights=False)
             self._replicas[B] = m
         src = self.src
         m.weight_tensor(0).view(B, self.N, self.D).copy_(src.weight_tensor(0).unsqueeze(0).expand(B, -1, -1))
@@ -146,7 +146,12 @@ class Explainer:
             state = _DenseAdam(self, init)
             batch_size = 1
         for s in range(0, len(triples), batch_size):
-            batch = _Batch(self, triples[s:s + batch_size])
+            chunk = triples[s:s + batch_size]
+            n_real = len(chunk)
+            if not shared_optimizer and n_real < batch_size and batch_size in self._replicas:
+                # pad the last batch to the size whose replica model already exists (padding results are dropped)
+                chunk = np.concatenate([chunk, np.repeat(chunk[:1], batch_size - n_real, axis=0)], 0)
+            batch = _Batch(self, chunk)
             logits = init[batch.edge_head, batch.edge_tail].contiguous()
             if not shared_optimizer:
                 state = _EdgeAdam(self, batch.graph.nnz)
@@ -155,7 +160,7 @@ class Explainer:
                 logits = state.current_logits(batch)
             top = self._topk(batch, logits, threshold, k)
             lv = loss.cpu().numpy()
-            results += [(a, b, float(lv[i])) for i, (a, b) in enumerate(top)]
+            results += [(a, b, float(lv[i])) for i, (a, b) in enumerate(top)][:n_real]
             if shared_optimizer:
                 state.reset_masks()
         return results

@@ -67,7 +67,7 @@ def _unbatch_idx(x, device):
 
 class IDDGCN_Model:
     def __init__(self, num_entities, num_relations, embedding_dim, output_dim, seed, mode=0, fold=0, *,
-                 num_layers=3, device=None, neg_weight=1.0):
+                 num_layers=3, device=None, neg_weight=1.0, init_weights=True):
         if embedding_dim != output_dim:
             raise ValueError("the reference wiring needs embedding_dim == output_dim (IDDGCN.py:62 on head_e)")
         if not torch.cuda.is_available():
@@ -96,7 +96,8 @@ class IDDGCN_Model:
         self.step_count = 0
         self._plans: dict = {}
         self.neg_path_template = "../datasets/prediction_datasets/mode{mode}_fold{fold}_X_train_neg.npy"
-        self._init_weights(seed)
+        if init_weights:          # replicas that get their weights copied in skip the random initialisation
+            self._init_weights(seed)
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):

@@ -6,20 +6,23 @@
 
 namespace iddgcn {
 
-constexpr int GT = 64;       // C tile is GT x GT
 constexpr int GK = 16;       // K step
 constexpr int GPAD = 4;      // keeps rows 16-byte aligned and spreads banks
 constexpr int GTHREADS = 256;
 
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(GTHREADS)
+// 256 threads as a 16 x 16 grid, each owning a TM x TN register micro-tile: the C tile is (16·TM) x (16·TN).
+//   <4,4>: 64 x 64   — narrow outputs (D = 64, W_alpha with N = R)
+//   <8,8>: 128 x 128 — D >= 128: 64 FMAs per 4 shared-memory vector loads instead of 16 per 2
+template <bool TA, bool TB, int TM, int TN>
+__global__ void __launch_bounds__(GTHREADS, (TM * TN > 16 ? 2 : 1))
     gemm_tile_kernel(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda, int64_t strideA,
                      const float* __restrict__ B, int64_t ldb, int64_t strideB, float* __restrict__ C, int64_t ldc,
                      int64_t strideC, int accumulate, int64_t k_chunk, int64_t ws_split_stride) {
   // grid: x = tile over M, y = tile over N, z = batch * splits (splits > 1 only for the split-K variant,
   // where C points at the workspace and ws_split_stride separates the partial results).
-  __shared__ __align__(16) float As[GK][GT + GPAD];
-  __shared__ __align__(16) float Bs[GK][GT + GPAD];
+  constexpr int BM = 16 * TM, BN = 16 * TN;
+  __shared__ __align__(16) float As[GK][BM + GPAD];
+  __shared__ __align__(16) float Bs[GK][BN + GPAD];
   const int splits = (k_chunk > 0 && K > 0) ? (int)((K + k_chunk - 1) / k_chunk) : 1;
   const int b = blockIdx.z / splits;
   const int sp = blockIdx.z % splits;
@@ -28,31 +31,31 @@ __global__ void __launch_bounds__(GTHREADS)
   A += (int64_t)b * strideA;
   B += (int64_t)b * strideB;
   C += (int64_t)b * strideC + (int64_t)sp * ws_split_stride;
-  const int64_t m0 = (int64_t)blockIdx.x * GT, n0 = (int64_t)blockIdx.y * GT;
+  const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
   const int tid = threadIdx.x;
   const int ty = tid / 16, tx = tid % 16;
-  float acc[4][4];
+  float acc[TM][TN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   for (int64_t k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
-    for (int i = 0; i < (GT * GK) / GTHREADS; ++i) {
+    for (int i = 0; i < (BM * GK) / GTHREADS; ++i) {
       const int idx = tid + i * GTHREADS;
       int m, k;
-      if (TA) { m = idx % GT; k = idx / GT; } else { k = idx % GK; m = idx / GK; }
+      if (TA) { m = idx % BM; k = idx / BM; } else { k = idx % GK; m = idx / GK; }
       const int64_t gm = m0 + m, gk = k0 + k;
       float v = 0.f;
       if (gm < M && gk < k_end) v = TA ? A[gk * lda + gm] : A[gm * lda + gk];
       As[k][m] = v;
     }
 #pragma unroll
-    for (int i = 0; i < (GT * GK) / GTHREADS; ++i) {
+    for (int i = 0; i < (BN * GK) / GTHREADS; ++i) {
       const int idx = tid + i * GTHREADS;
       int n, k;
-      if (TB) { k = idx % GK; n = idx / GK; } else { n = idx % GT; k = idx / GT; }
+      if (TB) { k = idx % GK; n = idx / GK; } else { n = idx % BN; k = idx / BN; }
       const int64_t gn = n0 + n, gk = k0 + k;
       float v = 0.f;
       if (gn < N && gk < k_end) v = TB ? B[gn * ldb + gk] : B[gk * ldb + gn];
@@ -61,24 +64,33 @@ __global__ void __launch_bounds__(GTHREADS)
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      // micro-tile rows/cols come in groups of 4 spaced 64 apart (ty*4 + 64*g), so that the 16 threads of a row of the
+      // thread grid read 16 consecutive float4 from shared memory (conflict-free) instead of strided ones
+      float a[TM], bb[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; i += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4 + (i / 4) * 64]);
+        a[i] = a4.x; a[i + 1] = a4.y; a[i + 2] = a4.z; a[i + 3] = a4.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      for (int j = 0; j < TN; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4 + (j / 4) * 64]);
+        bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t gm = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gm = m0 + ty * 4 + (i / 4) * 64 + (i % 4);
     if (gm >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t gn = n0 + tx * 4 + j;
+    for (int j = 0; j < TN; ++j) {
+      const int64_t gn = n0 + tx * 4 + (j / 4) * 64 + (j % 4);
       if (gn >= N) continue;
       float* c = C + gm * ldc + gn;
       *c = accumulate ? (*c + acc[i][j]) : acc[i][j];
@@ -111,27 +123,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA,
-             const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
-             bool accumulate, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
-  const int64_t gm = (M + GT - 1) / GT, gn = (N + GT - 1) / GT;
+template <int TM, int TN>
+static int gemm_launch(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                       int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc,
+                       int64_t strideC, int batch, int acc, cudaStream_t st) {
+  const int64_t gm = (M + 16 * TM - 1) / (16 * TM), gn = (N + 16 * TN - 1) / (16 * TN);
   IDD_CHECK(gm < 0x7fffffff && gn < 65536 && batch < 65536, IDDGCN_ELIMIT, "GEMM grid too large");
   dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)batch);
-  const int acc = accumulate ? 1 : 0;
   if (!transA && !transB)
-    gemm_tile_kernel<false, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+    gemm_tile_kernel<false, false, TM, TN><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
   else if (!transA && transB)
-    gemm_tile_kernel<false, true><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+    gemm_tile_kernel<false, true, TM, TN><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
   else if (transA && !transB)
-    gemm_tile_kernel<true, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+    gemm_tile_kernel<true, false, TM, TN><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
   else
-    gemm_tile_kernel<true, true><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
+    gemm_tile_kernel<true, true, TM, TN><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, acc, 0, 0);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }
 
+int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA,
+             const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
+             bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
+  const int acc = accumulate ? 1 : 0;
+  // big tiles only when they are filled and there are enough of them to cover the SMs
+  if (N >= 128 && M * batch >= 128 * (int64_t)sm_count())
+    return gemm_launch<8, 8>(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, acc, st);
+  return gemm_launch<4, 4>(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, acc, st);
+}
+
+// split-K tile edge: 128 when both output dimensions fill it (A and B are then read exactly once), else 64
+static inline int splitk_tile(int64_t M, int64_t N) { return (M >= 128 && N >= 128) ? 128 : 64; }
+
 static void splitk_shape(int64_t M, int64_t N, int64_t K, int batch, int* splits, int64_t* k_chunk) {
+  const int GT = splitk_tile(M, N);
   const int64_t tiles = ((M + GT - 1) / GT) * ((N + GT - 1) / GT) * batch;
   int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;   // ~2 waves of blocks
   int64_t max_by_k = (K + 4 * GK - 1) / (4 * GK);                  // at least 64 k per split
@@ -160,14 +186,37 @@ int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
   splitk_shape(M, N, K, batch, &splits, &chunk);
   if (K <= 0) splits = 1;
   const int64_t MN = M * N;
+  const int GT = splitk_tile(M, N);
   dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT), (unsigned)(batch * splits));
   IDD_CHECK(grid.y < 65536 && grid.z < 65536, IDDGCN_ELIMIT, "split-K GEMM grid too large");
   // partials: ws[b][s][M][N]  (strideC = splits*MN per batch, ws_split_stride = MN)
-  gemm_tile_kernel<true, false><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, workspace, N,
-                                                          (int64_t)splits * MN, 0, chunk, MN);
+  if (GT == 128)
+    gemm_tile_kernel<true, false, 8, 8><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, workspace,
+                                                                   N, (int64_t)splits * MN, 0, chunk, MN);
+  else
+    gemm_tile_kernel<true, false, 4, 4><<<grid, GTHREADS, 0, st>>>(M, N, K, A, lda, strideA, B, ldb, strideB, workspace,
+                                                                   N, (int64_t)splits * MN, 0, chunk, MN);
   IDD_LAUNCH_CHECK();
   dim3 rgrid((unsigned)((MN + 31) / 32), (unsigned)batch);
   splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(workspace, splits, MN, N, C, ldc, strideC, accumulate ? 1 : 0);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+// out[b][j][i] = in[b][i][j] for small square-ish matrices (weights): lets big-M products with a transposed weight
+// run through the faster non-transposed load path
+__global__ void transpose_small_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i % cols;
+  out[(size_t)b * rows * cols + (size_t)c * rows + r] = in[(size_t)b * rows * cols + i];
+}
+
+int transpose_small(const float* in, float* out, int rows, int cols, int batch, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return IDDGCN_OK;
+  transpose_small_kernel<<<dim3((unsigned)((rows * cols + 255) / 256), (unsigned)batch), 256, 0, st>>>(in, out, rows,
+                                                                                                      cols);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }

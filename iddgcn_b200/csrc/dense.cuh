@@ -22,4 +22,7 @@ int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
                        int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
                        bool accumulate, float* workspace, cudaStream_t st);
 
+// out[b] = in[b]ᵀ for small (weight-sized) row-major matrices [rows, cols]
+int transpose_small(const float* in, float* out, int rows, int cols, int batch, cudaStream_t st);
+
 }  // namespace iddgcn

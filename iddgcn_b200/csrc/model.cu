@@ -54,7 +54,7 @@ struct iddgcn_model {
   float* loss_dev = nullptr;
   // node-level workspace
   float *S = nullptr, *Z = nullptr, *dZ = nullptr, *dS = nullptr;
-  DevBuf<float> gemm_ws, small_ws, y_all, dy_all;
+  DevBuf<float> gemm_ws, small_ws, y_all, dy_all, wt_ws;   // wt_ws: transposed weights [R,D,D]
   std::unordered_map<const iddgcn_plan*, TripleWS> ws;
   // positives and negatives of a train step run as ONE batch of triples: (pos, neg) -> concatenated plan
   struct Merged { const iddgcn_plan* pos; const iddgcn_plan* neg; iddgcn_plan* both; };
@@ -193,7 +193,8 @@ static int triple_backward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, c
     // dZ_i += scatter(gate_i · dP)  (eq. 10)
     IDD_TRY(segment_scatter(p, dP, w->alpha[l], D, m->dZ + (size_t)l * m->plane(), 1, st));
     // d[Hin;Tin] = dP·W_selfᵀ (+ dz·W_alphaᵀ on the head side)  (eq. 9)
-    IDD_TRY(gemm_f32(false, true, 2 * T, D, D, dP, D, 0, m->P(lo.sk), D, 0, w->dHT[cur ^ 1], D, 0, 1, false, st));
+    IDD_TRY(transpose_small(m->P(lo.sk), m->wt_ws.p, (int)D, (int)D, 1, st));
+    IDD_TRY(gemm_f32(false, false, 2 * T, D, D, dP, D, 0, m->wt_ws.p, D, 0, w->dHT[cur ^ 1], D, 0, 1, false, st));
     IDD_TRY(layer_bwd_post(w->dz, m->P(lo.wa), T, D, m->R, w->dHT[cur ^ 1], st));
     cur ^= 1;
   }
@@ -225,7 +226,8 @@ static int node_backward(iddgcn_model* m, const iddgcn_graph* g, const float* va
     float* dZl = m->dZ + (size_t)l * m->plane();
     IDD_TRY(gemm_tn_splitk_f32(D, D, N, m->S, D, N * D, dZl, D, N * D, m->G(lo.rk), D, D * D, m->R, true,
                                m->gemm_ws.p, st));
-    IDD_TRY(gemm_f32(false, true, N, D, D, dZl, D, N * D, m->P(lo.rk), D, D * D, m->dS, D, N * D, m->R, l > 0, st));
+    IDD_TRY(transpose_small(m->P(lo.rk), m->wt_ws.p, (int)D, (int)D, m->R, st));
+    IDD_TRY(gemm_f32(false, false, N, D, D, dZl, D, N * D, m->wt_ws.p, D, D * D, m->dS, D, N * D, m->R, l > 0, st));
   }
   IDD_TRY(spmm_bwd_x_range(g, m->dS, D, vals, mode, m->G(m->lay.emb), 1, 0, N, st));
   if (dvals) IDD_TRY(sddmm_dispatch(g, m->dS, m->P(m->lay.emb), D, vals, mode, dvals, st));
@@ -312,6 +314,10 @@ int iddgcn_model_create(int64_t num_entities, int num_relations, int64_t dim, in
       (rc = alloc0(&m->Z, m->L * m->plane())) || (rc = alloc0(&m->dZ, m->L * m->plane())) ||
       (rc = alloc0(&m->loss_dev, 4)))
     return fail(rc);
+  if (m->wt_ws.ensure((size_t)m->R * m->D * m->D) != cudaSuccess) {
+    set_error("cudaMalloc(weight transpose scratch) failed");
+    return fail(IDDGCN_ENOMEM);
+  }
   if (cudaMalloc((void**)&m->step_dev, sizeof(int64_t)) != cudaSuccess ||
       cudaMemset(m->step_dev, 0, sizeof(int64_t)) != cudaSuccess) {
     set_error("cudaMalloc(step counter) failed");

@@ -437,6 +437,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dim", type=int, default=0, help="override the feature width D of the workload (default 128)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"],
                     help="multi-GPU exchange: NCCL collectives or hand-written NVSwitch multicast kernels")
     ap.add_argument("--mc-ctas", type=int, default=32, help="thread blocks of the multicast copy kernels")
@@ -446,6 +447,9 @@ def main():
         args.warmup = 3
     wl = dict(WORKLOADS[args.workload])
     wl["name"] = args.workload
+    if args.dim:
+        wl["D"] = args.dim
+        wl["dim_override"] = True
     wl["label"] = {
         "c3": "synthetic 1M-node / 20M-edge 2-relation directed graph, D=128 (BASELINE configs[2]); "
               "xP row-partitioned at --gpus P (configs[3] recipe, weak)",
@@ -453,6 +457,8 @@ def main():
         "small": "synthetic 100k-node / 2M-edge 2-relation graph, D=128 (smoke size)",
         "c3zipf": "config-3 shape with Zipf(1.2) destination degrees (skewed variant, SURVEY 8d)",
     }[args.workload]
+    if wl.get("dim_override"):
+        wl["label"] += f" [feature dim overridden to {wl['D']}]"
     if args.impl == "reference":
         run_reference(args, wl)
         return

@@ -25,6 +25,7 @@ _SIGNATURES = {
     "iddgcn_last_error": (C.c_char_p, []),
     "iddgcn_version": (C.c_char_p, []),
     "iddgcn_launch_count": (C.c_int64, []),
+    "iddgcn_pool_trim": (C.c_int, []),
     "iddgcn_graph_build": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, vp,
                                      C.POINTER(vp)]),
     "iddgcn_graph_destroy": (C.c_int, [vp]),

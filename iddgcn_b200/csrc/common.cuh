@@ -49,6 +49,11 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     IDD_CUDA(cudaGetLastError());                                                        \
   } while (0)
 
+// ---- pooled device memory (core.cu) -----------------------------------------
+cudaError_t pool_alloc(void** out, size_t bytes);
+void pool_free(void* p);   // synchronises the device, then caches the block for reuse
+void pool_trim();
+
 // ---- device memory RAII (internal workspaces only) -------------------------
 template <typename T>
 struct DevBuf {
@@ -59,7 +64,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     n = 0;
   }
@@ -68,11 +73,25 @@ struct DevBuf {
     if (count <= n && p) return cudaSuccess;
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    cudaError_t e = pool_alloc((void**)&p, count * sizeof(T));
     if (e == cudaSuccess) n = count; else p = nullptr;
     return e;
   }
   T* take() { T* q = p; p = nullptr; n = 0; return q; }
+};
+
+// One device allocation carved into 256-byte aligned pieces: cudaMalloc/cudaFree of multi-GB buffers cost more than the
+// build kernels themselves, so the whole build uses ONE temporary arena and TWO persistent blocks.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  template <typename T>
+  T* get(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += pad(count * sizeof(T));
+    return off <= cap ? p : nullptr;
+  }
 };
 
 inline int sm_count() {

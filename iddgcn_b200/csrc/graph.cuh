@@ -13,6 +13,8 @@ struct iddgcn_graph {
   int R = 0;
   int64_t nnz = 0;
   std::vector<int64_t> nnz_rel;
+  void* block_ptrs = nullptr;     // one allocation holding the row-pointer arrays below
+  void* block_edges = nullptr;    // one allocation holding the six per-edge arrays below
   int32_t* csr_rowptr = nullptr;  // [R*n_rows+1]
   int32_t* csr_col = nullptr;     // [nnz]
   int32_t* csr_row = nullptr;     // [nnz]
@@ -49,6 +51,7 @@ struct iddgcn_plan {
   int64_t T = 0;
   int64_t N = 0;
   int R = 0;
+  void* block = nullptr;        // one allocation holding every array below
   int32_t* head = nullptr;      // [T]
   int32_t* rel = nullptr;       // [T]
   int32_t* tail = nullptr;      // [T]

@@ -156,27 +156,23 @@ static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n 
 
 static inline unsigned blocks_for(size_t n, int threads);
 
-static int build_heavy_list(const int32_t* ptr, size_t rows, cudaStream_t st, iddgcn_graph::HeavyList* out) {
-  DevBuf<uint32_t> hub, seg, scr;
-  IDD_CUDA(hub.ensure(rows + 1));
-  IDD_CUDA(seg.ensure(rows + 1));
-  IDD_CUDA(scr.ensure(scan_scratch_elems(rows + 1)));
-  heavy_flag_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub.p, seg.p);
+static int build_heavy_list(const int32_t* ptr, size_t rows, uint32_t* hub, uint32_t* seg, uint32_t* scr,
+                            cudaStream_t st, iddgcn_graph::HeavyList* out) {
+  heavy_flag_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub, seg);
   IDD_LAUNCH_CHECK();
-  IDD_TRY(exclusive_scan_u32(hub.p, hub.p, rows + 1, scr.p, st));
-  IDD_TRY(exclusive_scan_u32(seg.p, seg.p, rows + 1, scr.p, st));
+  IDD_TRY(exclusive_scan_u32(hub, hub, rows + 1, scr, st));
+  IDD_TRY(exclusive_scan_u32(seg, seg, rows + 1, scr, st));
   uint32_t H = 0, S = 0;
-  IDD_CUDA(cudaMemcpyAsync(&H, hub.p + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  IDD_CUDA(cudaMemcpyAsync(&S, seg.p + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaMemcpyAsync(&H, hub + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaMemcpyAsync(&S, seg + rows, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   IDD_CUDA(cudaStreamSynchronize(st));
   out->H = (int)H;
   out->total_segs = (int)S;
   if (H) {
-    IDD_CUDA(cudaMalloc((void**)&out->rows, (size_t)H * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&out->segptr, ((size_t)H + 1) * sizeof(int32_t)));
-    heavy_compact_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub.p, seg.p, out->rows, out->segptr, H);
+    IDD_CUDA(pool_alloc((void**)&out->rows, (size_t)H * sizeof(int32_t)));
+    IDD_CUDA(pool_alloc((void**)&out->segptr, ((size_t)H + 1) * sizeof(int32_t)));
+    heavy_compact_kernel<<<blocks_for(rows + 1, 256), 256, 0, st>>>(ptr, rows, hub, seg, out->rows, out->segptr, H);
     IDD_LAUNCH_CHECK();
-    IDD_CUDA(cudaStreamSynchronize(st));
   }
   return IDDGCN_OK;
 }
@@ -194,136 +190,151 @@ static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device,
   IDD_CHECK(L.total() + 1 <= 63, IDDGCN_ELIMIT, "key does not fit 63 bits (N=%lld, R=%d)", (long long)N, R);
   const size_t csr_segs = (size_t)R * (size_t)n_rows;
   const size_t csc_segs = (size_t)R * (size_t)N;
+  const size_t Nz = (size_t)N;
   IDD_CHECK(M < (int64_t)0x7fffff00 && csc_segs < (size_t)0x7fffff00 && csr_segs < (size_t)0x7fffff00, IDDGCN_ELIMIT,
             "graph exceeds int32 index range (M=%lld, R*N=%zu)", (long long)M, csc_segs);
 
   g->N = N; g->n_rows = n_rows; g->row_lo = row_lo; g->R = R;
   g->nnz_rel.assign(R, 0);
   IDD_CUDA(cudaGetDevice(&g->device));
-  IDD_CUDA(cudaMalloc((void**)&g->csr_rowptr, (csr_segs + 1) * sizeof(int32_t)));
-  IDD_CUDA(cudaMalloc((void**)&g->csc_rowptr, (csc_segs + 1) * sizeof(int32_t)));
-  IDD_CUDA(cudaMalloc((void**)&g->rel_sums_scratch, (size_t)(R > 0 ? R : 1) * sizeof(float)));
 
-  const size_t Mz = (size_t)M;
-  DevBuf<int64_t> trip_tmp;
-  const int64_t* triples = triples_in;
-  if (!on_device && Mz) {
-    IDD_CUDA(trip_tmp.ensure(Mz * 3));
-    IDD_CUDA(cudaMemcpyAsync(trip_tmp.p, triples_in, Mz * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    triples = trip_tmp.p;
+  // persistent block 1: the three row-pointer arrays + the per-relation scratch
+  {
+    const size_t bytes = Arena::pad((csr_segs + 1) * 4) + Arena::pad((csc_segs + 1) * 4) + Arena::pad((Nz + 1) * 4) +
+                         Arena::pad((size_t)(R > 0 ? R : 1) * 4);
+    IDD_CUDA(pool_alloc(&g->block_ptrs, bytes));
+    Arena a{reinterpret_cast<char*>(g->block_ptrs), bytes, 0};
+    g->csr_rowptr = a.get<int32_t>(csr_segs + 1);
+    g->csc_rowptr = a.get<int32_t>(csc_segs + 1);
+    g->bwd_rowptr = a.get<int32_t>(Nz + 1);
+    g->rel_sums_scratch = a.get<float>((size_t)(R > 0 ? R : 1));
   }
 
-  size_t nnz = 0;
-  DevBuf<uint64_t> kA, kB;
-  DevBuf<uint32_t> vA, vB, hist, scratch, flags;
-  DevBuf<int> err;
-  uint64_t* ukeys = nullptr;
-  if (Mz) {
-    const RadixSortPlan plan = radix_sort_plan(Mz);
-    IDD_CUDA(kA.ensure(Mz));
-    IDD_CUDA(kB.ensure(Mz));
-    IDD_CUDA(hist.ensure(plan.hist_elems));
-    const size_t scr = plan.scratch_elems > scan_scratch_elems(Mz + 1) ? plan.scratch_elems : scan_scratch_elems(Mz + 1);
-    IDD_CUDA(scratch.ensure(scr));
-    IDD_CUDA(flags.ensure(Mz + 1));
-    IDD_CUDA(err.ensure(1));
-    IDD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+  // temporary arena
+  const size_t Mz = (size_t)M;
+  const size_t Ma = Mz ? Mz : 1;
+  const RadixSortPlan plan = radix_sort_plan(Ma);
+  const size_t max_rows = (csr_segs > Nz ? csr_segs : Nz);
+  size_t scan_n = Mz + 1;
+  if (max_rows + 1 > scan_n) scan_n = max_rows + 1;
+  size_t scr_elems = scan_scratch_elems(scan_n);
+  if (plan.scratch_elems > scr_elems) scr_elems = plan.scratch_elems;
+  size_t tmp_bytes = 2 * Arena::pad(Ma * 8) + 2 * Arena::pad(Ma * 4) + Arena::pad(plan.hist_elems * 4) +
+                     Arena::pad(scr_elems * 4) + Arena::pad((Mz + 1) * 4) + 2 * Arena::pad((max_rows + 1) * 4) +
+                     Arena::pad(256);
+  if (!on_device && Mz) tmp_bytes += Arena::pad(Mz * 3 * 8);
+  DevBuf<char> tmp;
+  IDD_CUDA(tmp.ensure(tmp_bytes));
+  Arena ar{tmp.p, tmp_bytes, 0};
+  uint64_t* kA = ar.get<uint64_t>(Ma);
+  uint64_t* kB = ar.get<uint64_t>(Ma);
+  uint32_t* vA = ar.get<uint32_t>(Ma);
+  uint32_t* vB = ar.get<uint32_t>(Ma);
+  uint32_t* hist = ar.get<uint32_t>(plan.hist_elems);
+  uint32_t* scratch = ar.get<uint32_t>(scr_elems);
+  uint32_t* flags = ar.get<uint32_t>(Mz + 1);
+  uint32_t* hub_tmp = ar.get<uint32_t>(max_rows + 1);
+  uint32_t* seg_tmp = ar.get<uint32_t>(max_rows + 1);
+  int* err = ar.get<int>(64);
+  const int64_t* triples = triples_in;
+  if (!on_device && Mz) {
+    int64_t* trip_tmp = ar.get<int64_t>(Mz * 3);
+    IDD_CHECK(trip_tmp != nullptr, IDDGCN_ENOMEM, "internal: arena too small");
+    IDD_CUDA(cudaMemcpyAsync(trip_tmp, triples_in, Mz * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    triples = trip_tmp;
+  }
+  IDD_CHECK(err != nullptr && ar.off <= ar.cap, IDDGCN_ENOMEM, "internal: arena too small");
 
-    pack_keys_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(triples, Mz, N, R, row_lo, row_hi, L, kA.p, err.p);
+  size_t nnz = 0;
+  uint64_t* ukeys = nullptr;
+  uint64_t* sorted = nullptr;
+  if (Mz) {
+    IDD_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    pack_keys_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(triples, Mz, N, R, row_lo, row_hi, L, kA, err);
     IDD_LAUNCH_CHECK();
-    uint64_t* sorted = nullptr;
-    IDD_TRY(radix_sort_u64(kA.p, kB.p, nullptr, nullptr, Mz, L.total() + 1, plan, hist.p, scratch.p, st, &sorted,
-                           nullptr));
-    uint64_t* other = (sorted == kA.p) ? kB.p : kA.p;
+    IDD_TRY(radix_sort_u64(kA, kB, nullptr, nullptr, Mz, L.total() + 1, plan, hist, scratch, st, &sorted, nullptr));
+    uint64_t* other = (sorted == kA) ? kB : kA;
     const uint64_t invalid = 1ull << L.total();
-    unique_flag_kernel<<<blocks_for(Mz + 1, 256), 256, 0, st>>>(sorted, Mz, invalid, flags.p);
+    unique_flag_kernel<<<blocks_for(Mz + 1, 256), 256, 0, st>>>(sorted, Mz, invalid, flags);
     IDD_LAUNCH_CHECK();
-    IDD_TRY(exclusive_scan_u32(flags.p, flags.p, Mz + 1, scratch.p, st));
-    unique_compact_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(sorted, Mz, invalid, flags.p, other);
+    IDD_TRY(exclusive_scan_u32(flags, flags, Mz + 1, scratch, st));
+    unique_compact_kernel<<<blocks_for(Mz, 256), 256, 0, st>>>(sorted, Mz, invalid, flags, other);
     IDD_LAUNCH_CHECK();
     uint32_t nnz32 = 0;
     int herr = 0;
-    IDD_CUDA(cudaMemcpyAsync(&nnz32, flags.p + Mz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    IDD_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IDD_CUDA(cudaMemcpyAsync(&nnz32, flags + Mz, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    IDD_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     IDD_CUDA(cudaStreamSynchronize(st));
     IDD_CHECK(herr == 0, IDDGCN_ERANGE, "triples contain an entity index outside [0, %lld)", (long long)N);
     nnz = nnz32;
     ukeys = other;  // `sorted` is now free to be reused
-    // CSR
-    const size_t alloc_e = nnz ? nnz : 1;
-    IDD_CUDA(cudaMalloc((void**)&g->csr_col, alloc_e * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csr_row, alloc_e * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csc_row, alloc_e * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csc_perm, alloc_e * sizeof(int32_t)));
+  }
+
+  // persistent block 2: the six per-edge arrays
+  {
+    const size_t ne = nnz ? nnz : 1;
+    const size_t bytes = 6 * Arena::pad(ne * 4);
+    IDD_CUDA(pool_alloc(&g->block_edges, bytes));
+    Arena a{reinterpret_cast<char*>(g->block_edges), bytes, 0};
+    g->csr_col = a.get<int32_t>(ne);
+    g->csr_row = a.get<int32_t>(ne);
+    g->csc_row = a.get<int32_t>(ne);
+    g->csc_perm = a.get<int32_t>(ne);
+    g->bwd_src = a.get<int32_t>(ne);
+    g->bwd_perm = a.get<int32_t>(ne);
+  }
+
+  if (nnz) {
     segment_ptr_kernel<<<blocks_for(csr_segs + 1, 256), 256, 0, st>>>(ukeys, nnz, csr_segs, (uint64_t)n_rows,
                                                                       L.bh + L.bt, L.bt, g->csr_rowptr);
     IDD_LAUNCH_CHECK();
-    if (nnz) {
-      IDD_CUDA(vA.ensure(nnz));
-      IDD_CUDA(vB.ensure(nnz));
-      uint64_t* keys2 = sorted;
-      decode_csr_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(ukeys, nnz, L, g->csr_col, g->csr_row, keys2, vA.p);
-      IDD_LAUNCH_CHECK();
-      const RadixSortPlan plan2 = radix_sort_plan(nnz);  // nnz <= M: hist/scratch are large enough
-      uint64_t* s2 = nullptr;
-      uint32_t* sv = nullptr;
-      IDD_TRY(radix_sort_u64(keys2, ukeys, vA.p, vB.p, nnz, L.total(), plan2, hist.p, scratch.p, st, &s2, &sv));
-      decode_csc_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(s2, sv, nnz, L, g->csc_row, g->csc_perm);
-      IDD_LAUNCH_CHECK();
-      segment_ptr_kernel<<<blocks_for(csc_segs + 1, 256), 256, 0, st>>>(s2, nnz, csc_segs, (uint64_t)N, L.bh + L.bt,
-                                                                        L.bh, g->csc_rowptr);
-      IDD_LAUNCH_CHECK();
-    } else {
-      IDD_CUDA(cudaMemsetAsync(g->csc_rowptr, 0, (csc_segs + 1) * sizeof(int32_t), st));
-    }
+    uint64_t* keys2 = sorted;
+    decode_csr_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(ukeys, nnz, L, g->csr_col, g->csr_row, keys2, vA);
+    IDD_LAUNCH_CHECK();
+    const RadixSortPlan plan2 = radix_sort_plan(nnz);  // nnz <= M: hist/scratch are large enough
+    uint64_t* s2 = nullptr;
+    uint32_t* sv = nullptr;
+    IDD_TRY(radix_sort_u64(keys2, ukeys, vA, vB, nnz, L.total(), plan2, hist, scratch, st, &s2, &sv));
+    decode_csc_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(s2, sv, nnz, L, g->csc_row, g->csc_perm);
+    IDD_LAUNCH_CHECK();
+    segment_ptr_kernel<<<blocks_for(csc_segs + 1, 256), 256, 0, st>>>(s2, nnz, csc_segs, (uint64_t)N, L.bh + L.bt, L.bh,
+                                                                      g->csc_rowptr);
+    IDD_LAUNCH_CHECK();
   } else {
-    IDD_CUDA(cudaMalloc((void**)&g->csr_col, sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csr_row, sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csc_row, sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->csc_perm, sizeof(int32_t)));
     IDD_CUDA(cudaMemsetAsync(g->csr_rowptr, 0, (csr_segs + 1) * sizeof(int32_t), st));
     IDD_CUDA(cudaMemsetAsync(g->csc_rowptr, 0, (csc_segs + 1) * sizeof(int32_t), st));
   }
   // node-major backward view
   {
-    const size_t Nz = (size_t)N;
-    IDD_CUDA(cudaMalloc((void**)&g->bwd_rowptr, (Nz + 1) * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->bwd_src, (nnz ? nnz : 1) * sizeof(int32_t)));
-    IDD_CUDA(cudaMalloc((void**)&g->bwd_perm, (nnz ? nnz : 1) * sizeof(int32_t)));
-    DevBuf<uint32_t> scr2;
-    IDD_CUDA(scr2.ensure(scan_scratch_elems(Nz + 1)));
     uint32_t* cnt = reinterpret_cast<uint32_t*>(g->bwd_rowptr);
     bwd_count_kernel<<<blocks_for(Nz + 1, 256), 256, 0, st>>>(g->csc_rowptr, Nz, R, cnt);
     IDD_LAUNCH_CHECK();
-    IDD_TRY(exclusive_scan_u32(cnt, cnt, Nz + 1, scr2.p, st));
+    IDD_TRY(exclusive_scan_u32(cnt, cnt, Nz + 1, scratch, st));
     if (nnz) {
       bwd_fill_kernel<<<blocks_for(Nz * (size_t)R, 256), 256, 0, st>>>(g->csc_rowptr, g->csc_row, g->csc_perm, Nz, R,
                                                                        n_rows, g->bwd_rowptr, g->bwd_src, g->bwd_perm);
       IDD_LAUNCH_CHECK();
     }
-    IDD_CUDA(cudaStreamSynchronize(st));  // scr2 is freed at the end of this scope
   }
-  IDD_TRY(build_heavy_list(g->csr_rowptr, csr_segs, st, &g->heavy_fwd));
-  IDD_TRY(build_heavy_list(g->bwd_rowptr, (size_t)N, st, &g->heavy_bwd));
+  IDD_TRY(build_heavy_list(g->csr_rowptr, csr_segs, hub_tmp, seg_tmp, scratch, st, &g->heavy_fwd));
+  IDD_TRY(build_heavy_list(g->bwd_rowptr, Nz, hub_tmp, seg_tmp, scratch, st, &g->heavy_bwd));
   g->nnz = (int64_t)nnz;
   // per-relation counts: R+1 strided reads of the CSR row pointer
   std::vector<int32_t> bounds(R + 1, 0);
   for (int r = 0; r <= R; ++r)
     IDD_CUDA(cudaMemcpyAsync(&bounds[r], g->csr_rowptr + (size_t)r * n_rows, sizeof(int32_t), cudaMemcpyDeviceToHost,
                              st));
-  IDD_CUDA(cudaStreamSynchronize(st));
+  IDD_CUDA(cudaStreamSynchronize(st));  // also: every kernel using the arena has finished before it is freed
   for (int r = 0; r < R; ++r) g->nnz_rel[r] = (int64_t)bounds[r + 1] - bounds[r];
   return IDDGCN_OK;
 }
 
 static void graph_free(iddgcn_graph* g) {
   if (!g) return;
-  cudaFree(g->csr_rowptr); cudaFree(g->csr_col); cudaFree(g->csr_row);
-  cudaFree(g->csc_rowptr); cudaFree(g->csc_row); cudaFree(g->csc_perm);
-  cudaFree(g->bwd_rowptr); cudaFree(g->bwd_src); cudaFree(g->bwd_perm);
-  cudaFree(g->rel_sums_scratch);
-  cudaFree(g->heavy_fwd.rows); cudaFree(g->heavy_fwd.segptr);
-  cudaFree(g->heavy_bwd.rows); cudaFree(g->heavy_bwd.segptr);
+  pool_free(g->block_ptrs);    // csr_rowptr, csc_rowptr, bwd_rowptr, rel_sums_scratch are views into it
+  pool_free(g->block_edges);   // csr_col, csr_row, csc_row, csc_perm, bwd_src, bwd_perm likewise
+  pool_free(g->heavy_fwd.rows); pool_free(g->heavy_fwd.segptr);
+  pool_free(g->heavy_bwd.rows); pool_free(g->heavy_bwd.segptr);
   cudaFree(g->heavy_ws);
   cudaFree(g->host_ws);
   for (int i = 0; i < 3; ++i) {
@@ -383,15 +394,15 @@ static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64
   p->T = T; p->N = N; p->R = R;
   const size_t Tz = (size_t)T;
   const size_t Ta = Tz ? Tz : 1;
-  IDD_CUDA(cudaMalloc((void**)&p->head, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->rel, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->tail, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_head_perm, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_tail_perm, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_rel_perm, Ta * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_head_ptr, ((size_t)N + 1) * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_tail_ptr, ((size_t)N + 1) * 4));
-  IDD_CUDA(cudaMalloc((void**)&p->by_rel_ptr, ((size_t)R + 1) * 4));
+  {  // one persistent allocation for the nine arrays
+    const size_t bytes = 6 * Arena::pad(Ta * 4) + 2 * Arena::pad(((size_t)N + 1) * 4) + Arena::pad(((size_t)R + 1) * 4);
+    IDD_CUDA(pool_alloc(&p->block, bytes));
+    Arena a{reinterpret_cast<char*>(p->block), bytes, 0};
+    p->head = a.get<int32_t>(Ta); p->rel = a.get<int32_t>(Ta); p->tail = a.get<int32_t>(Ta);
+    p->by_head_perm = a.get<int32_t>(Ta); p->by_tail_perm = a.get<int32_t>(Ta); p->by_rel_perm = a.get<int32_t>(Ta);
+    p->by_head_ptr = a.get<int32_t>((size_t)N + 1); p->by_tail_ptr = a.get<int32_t>((size_t)N + 1);
+    p->by_rel_ptr = a.get<int32_t>((size_t)R + 1);
+  }
   if (!Tz) {
     IDD_CUDA(cudaMemsetAsync(p->by_head_ptr, 0, ((size_t)N + 1) * 4, st));
     IDD_CUDA(cudaMemsetAsync(p->by_tail_ptr, 0, ((size_t)N + 1) * 4, st));
@@ -399,49 +410,51 @@ static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64
     IDD_CUDA(cudaStreamSynchronize(st));
     return IDDGCN_OK;
   }
-  DevBuf<int64_t> tmp;
+  const RadixSortPlan plan = radix_sort_plan(Tz);
+  size_t tmp_bytes = 2 * Arena::pad(Tz * 8) + 2 * Arena::pad(Tz * 4) + Arena::pad(plan.hist_elems * 4) +
+                     Arena::pad(plan.scratch_elems * 4) + Arena::pad(256);
+  if (!on_device) tmp_bytes += Arena::pad(Tz * 3 * 8);
+  DevBuf<char> tmp;
+  IDD_CUDA(tmp.ensure(tmp_bytes));
+  Arena ar{tmp.p, tmp_bytes, 0};
+  uint64_t* kA = ar.get<uint64_t>(Tz);
+  uint64_t* kB = ar.get<uint64_t>(Tz);
+  uint32_t* vA = ar.get<uint32_t>(Tz);
+  uint32_t* vB = ar.get<uint32_t>(Tz);
+  uint32_t* hist = ar.get<uint32_t>(plan.hist_elems);
+  uint32_t* scratch = ar.get<uint32_t>(plan.scratch_elems);
+  int* err = ar.get<int>(64);
   const int64_t *dh = head, *dr = rel, *dt = tail;
   if (!on_device) {
-    IDD_CUDA(tmp.ensure(Tz * 3));
-    IDD_CUDA(cudaMemcpyAsync(tmp.p, head, Tz * 8, cudaMemcpyHostToDevice, st));
-    IDD_CUDA(cudaMemcpyAsync(tmp.p + Tz, rel, Tz * 8, cudaMemcpyHostToDevice, st));
-    IDD_CUDA(cudaMemcpyAsync(tmp.p + 2 * Tz, tail, Tz * 8, cudaMemcpyHostToDevice, st));
-    dh = tmp.p; dr = tmp.p + Tz; dt = tmp.p + 2 * Tz;
+    int64_t* t3 = ar.get<int64_t>(Tz * 3);
+    IDD_CHECK(t3 != nullptr, IDDGCN_ENOMEM, "internal: arena too small");
+    IDD_CUDA(cudaMemcpyAsync(t3, head, Tz * 8, cudaMemcpyHostToDevice, st));
+    IDD_CUDA(cudaMemcpyAsync(t3 + Tz, rel, Tz * 8, cudaMemcpyHostToDevice, st));
+    IDD_CUDA(cudaMemcpyAsync(t3 + 2 * Tz, tail, Tz * 8, cudaMemcpyHostToDevice, st));
+    dh = t3; dr = t3 + Tz; dt = t3 + 2 * Tz;
   }
-  DevBuf<int> err;
-  IDD_CUDA(err.ensure(1));
-  IDD_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
-  plan_pack_kernel<<<blocks_for(Tz, 256), 256, 0, st>>>(dh, dr, dt, Tz, N, R, p->head, p->rel, p->tail, err.p);
+  IDD_CHECK(err != nullptr && ar.off <= ar.cap, IDDGCN_ENOMEM, "internal: arena too small");
+  IDD_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  plan_pack_kernel<<<blocks_for(Tz, 256), 256, 0, st>>>(dh, dr, dt, Tz, N, R, p->head, p->rel, p->tail, err);
   IDD_LAUNCH_CHECK();
-  int herr = 0;
-  IDD_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  IDD_CUDA(cudaStreamSynchronize(st));
-  IDD_CHECK(herr == 0, IDDGCN_ERANGE, "triple index outside [0,%lld) or relation outside [0,%d)", (long long)N, R);
-
-  const RadixSortPlan plan = radix_sort_plan(Tz);
-  DevBuf<uint64_t> kA, kB;
-  DevBuf<uint32_t> vA, vB, hist, scratch;
-  IDD_CUDA(kA.ensure(Tz)); IDD_CUDA(kB.ensure(Tz)); IDD_CUDA(vA.ensure(Tz)); IDD_CUDA(vB.ensure(Tz));
-  IDD_CUDA(hist.ensure(plan.hist_elems));
-  IDD_CUDA(scratch.ensure(plan.scratch_elems));
   const int bn = ceil_log2_u64((uint64_t)(N > 1 ? N - 1 : 1));
   const int brr = ceil_log2_u64((uint64_t)(R > 1 ? R - 1 : 1));
-  IDD_TRY(plan_sort_by(p->head, Tz, (size_t)N, bn, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
-                       p->by_head_perm, p->by_head_ptr));
-  IDD_TRY(plan_sort_by(p->tail, Tz, (size_t)N, bn, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
-                       p->by_tail_perm, p->by_tail_ptr));
-  IDD_TRY(plan_sort_by(p->rel, Tz, (size_t)R, brr, kA.p, kB.p, vA.p, vB.p, plan, hist.p, scratch.p, st,
-                       p->by_rel_perm, p->by_rel_ptr));
-  IDD_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
+  IDD_TRY(plan_sort_by(p->head, Tz, (size_t)N, bn, kA, kB, vA, vB, plan, hist, scratch, st, p->by_head_perm,
+                       p->by_head_ptr));
+  IDD_TRY(plan_sort_by(p->tail, Tz, (size_t)N, bn, kA, kB, vA, vB, plan, hist, scratch, st, p->by_tail_perm,
+                       p->by_tail_ptr));
+  IDD_TRY(plan_sort_by(p->rel, Tz, (size_t)R, brr, kA, kB, vA, vB, plan, hist, scratch, st, p->by_rel_perm,
+                       p->by_rel_ptr));
+  int herr = 0;
+  IDD_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  IDD_CUDA(cudaStreamSynchronize(st));  // the arena is freed on return
+  IDD_CHECK(herr == 0, IDDGCN_ERANGE, "triple index outside [0,%lld) or relation outside [0,%d)", (long long)N, R);
   return IDDGCN_OK;
 }
 
 static void plan_free(iddgcn_plan* p) {
   if (!p) return;
-  cudaFree(p->head); cudaFree(p->rel); cudaFree(p->tail);
-  cudaFree(p->by_head_perm); cudaFree(p->by_head_ptr);
-  cudaFree(p->by_tail_perm); cudaFree(p->by_tail_ptr);
-  cudaFree(p->by_rel_perm); cudaFree(p->by_rel_ptr);
+  pool_free(p->block);   // the nine index arrays are views into it
   delete p;
 }
 

@@ -31,6 +31,7 @@ struct ParamLayout {
 
 struct TripleWS {
   int64_t T = 0;
+  const iddgcn_plan* owner = nullptr;  // the plan whose activations are cached here (forward -> backward pairing)
   std::vector<float*> HT;     // L+1 buffers (2,T,D)
   std::vector<float*> alpha;  // L buffers (T,R)
   float* dHT[2] = {nullptr, nullptr};
@@ -40,7 +41,7 @@ struct TripleWS {
     for (float* p : HT) cudaFree(p);
     for (float* p : alpha) cudaFree(p);
     cudaFree(dHT[0]); cudaFree(dHT[1]); cudaFree(dz); cudaFree(y);
-    HT.clear(); alpha.clear(); dHT[0] = dHT[1] = dz = y = nullptr; T = 0;
+    HT.clear(); alpha.clear(); dHT[0] = dHT[1] = dz = y = nullptr; T = 0; owner = nullptr;
   }
 };
 
@@ -55,7 +56,9 @@ struct iddgcn_model {
   // node-level workspace
   float *S = nullptr, *Z = nullptr, *dZ = nullptr, *dS = nullptr;
   DevBuf<float> gemm_ws, small_ws, y_all, dy_all, wt_ws;   // wt_ws: transposed weights [R,D,D]
-  std::unordered_map<const iddgcn_plan*, TripleWS> ws;
+  // activation workspaces are keyed by the NUMBER of triples, not by plan: a stream of same-sized plans (explainer
+  // batches) reuses one set of buffers instead of allocating and freeing ~13 of them per plan
+  std::unordered_map<int64_t, TripleWS> ws;
   // positives and negatives of a train step run as ONE batch of triples: (pos, neg) -> concatenated plan
   struct Merged { const iddgcn_plan* pos; const iddgcn_plan* neg; iddgcn_plan* both; };
   std::vector<Merged> merged;
@@ -103,7 +106,7 @@ static void model_free(iddgcn_model* m) {
 }
 
 static int ensure_triple_ws(iddgcn_model* m, const iddgcn_plan* p, TripleWS** out) {
-  TripleWS& w = m->ws[p];
+  TripleWS& w = m->ws[p->T];
   if (w.T != p->T || w.HT.empty()) {
     w.release();
     const size_t td = (size_t)(p->T ? p->T : 1) * m->D;
@@ -159,6 +162,7 @@ static int node_forward(iddgcn_model* m, const iddgcn_graph* g, const float* val
 }
 
 static int triple_forward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, float* y_out, cudaStream_t st) {
+  w->owner = p;
   if (p->T == 0) return IDDGCN_OK;
   IDD_TRY(gather_embeddings(p, m->P(m->lay.emb), m->D, w->HT[0], st));
   for (int l = 0; l < m->L; ++l) {
@@ -363,17 +367,13 @@ int iddgcn_model_buffers(iddgcn_model_t* m, float** params, float** grads, float
 // drop the cached activations of a plan (call before destroying the plan)
 int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p) {
   IDD_CHECK(m != nullptr, IDDGCN_EINVAL, "model is NULL");
-  auto it = m->ws.find(p);
-  if (it != m->ws.end()) {
-    cudaDeviceSynchronize();
-    it->second.release();
-    m->ws.erase(it);
-  }
+  for (auto& kv : m->ws)
+    if (kv.second.owner == p) kv.second.owner = nullptr;   // buffers stay for the next plan of this size
   for (size_t i = 0; i < m->merged.size();) {
     if (m->merged[i].pos == p || m->merged[i].neg == p) {
       cudaDeviceSynchronize();
-      auto it2 = m->ws.find(m->merged[i].both);
-      if (it2 != m->ws.end()) { it2->second.release(); m->ws.erase(it2); }
+      for (auto& kv : m->ws)
+        if (kv.second.owner == m->merged[i].both) kv.second.owner = nullptr;
       plan_destroy_internal(m->merged[i].both);
       m->merged.erase(m->merged.begin() + i);
     } else {
@@ -406,8 +406,8 @@ int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddg
   IDD_TRY(check_compat(m, g, p));
   IDD_CHECK(dy != nullptr || p->T == 0, IDDGCN_EINVAL, "dy is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  auto it = m->ws.find(p);
-  IDD_CHECK(it != m->ws.end() && it->second.T == p->T, IDDGCN_EINVAL,
+  auto it = m->ws.find(p->T);
+  IDD_CHECK(it != m->ws.end() && it->second.T == p->T && it->second.owner == p, IDDGCN_EINVAL,
             "model_backward must follow model_forward on the same plan");
   IDD_TRY(zero_step_buffers(m, zero_grads != 0, st));
   IDD_TRY(triple_backward(m, p, &it->second, it->second.y, dy, st));

@@ -50,6 +50,8 @@ class _Batch:
         shift = torch.arange(B, device=dev, dtype=torch.int64) * N
         self.plan = Plan(h + shift, r, t + shift, N * B, R, device=dev)
         self.model = ex._replica(B)
+        import weakref
+        self.plan._models.append(weakref.ref(self.model))   # closing the plan drops the activations cached for it
         d = self.graph.device_arrays()
         rows = d["csr_row"].to(torch.int64)
         cols = d["csr_col"].to(torch.int64)
@@ -58,6 +60,12 @@ class _Batch:
         self.edge_tail = cols % N
         offs = torch.from_numpy(self.graph.rel_offsets).to(dev)
         self.edge_rel = torch.bucketize(torch.arange(self.graph.nnz, device=dev), offs[1:], right=True)
+
+    def close(self):
+        """Release the device handles now instead of whenever the garbage collector gets to them."""
+        self.plan.close()
+        self.graph._dev_cache = {}
+        self.graph.close()
 
 
 class Explainer:
@@ -69,6 +77,7 @@ class Explainer:
         self._lib = load()
         self.graph = Graph(adjacency_data, self.N, self.R, device=self.device)
         self._replicas: dict[int, IDDGCN_Model] = {}
+        self.timings = None      # set to {} to collect a per-phase wall-clock breakdown (adds synchronisations)
 
     def _replica(self, B: int) -> IDDGCN_Model:
         """Model over B·N entities whose embedding table is the trained one tiled B times."""
@@ -145,7 +154,16 @@ class Explainer:
         if shared_optimizer:
             state = _DenseAdam(self, init)
             batch_size = 1
+        import time as _time
+
+        def _tick(name, t0):
+            if self.timings is not None:
+                torch.cuda.synchronize(self.device)
+                self.timings[name] = self.timings.get(name, 0.0) + _time.perf_counter() - t0
+            return _time.perf_counter()
+
         for s in range(0, len(triples), batch_size):
+            t0 = _time.perf_counter()
             chunk = triples[s:s + batch_size]
             n_real = len(chunk)
             if not shared_optimizer and n_real < batch_size and batch_size in self._replicas:
@@ -153,14 +171,18 @@ class Explainer:
                 chunk = np.concatenate([chunk, np.repeat(chunk[:1], batch_size - n_real, axis=0)], 0)
             batch = _Batch(self, chunk)
             logits = init[batch.edge_head, batch.edge_tail].contiguous()
+            t0 = _tick("batch_assembly", t0)
             if not shared_optimizer:
                 state = _EdgeAdam(self, batch.graph.nnz)
             _, loss = self._optimise(batch, logits, epochs, learning_rate, structure_target, state)
+            t0 = _tick("mask_optimisation", t0)
             if shared_optimizer:
                 logits = state.current_logits(batch)
             top = self._topk(batch, logits, threshold, k)
             lv = loss.cpu().numpy()
             results += [(a, b, float(lv[i])) for i, (a, b) in enumerate(top)][:n_real]
+            batch.close()
+            t0 = _tick("top_k", t0)
             if shared_optimizer:
                 state.reset_masks()
         return results

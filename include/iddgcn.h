@@ -57,6 +57,9 @@ const char* iddgcn_version(void);
 /* number of kernel launches issued by this library on the calling thread's
  * handles since process start (bench.py's gpu_launches). */
 int64_t iddgcn_launch_count(void);
+/* Graph / plan handles and build temporaries come from a small caching pool (cudaFree costs tens of ms in a
+ * context that maps several GB); this returns every cached block to the driver. */
+int iddgcn_pool_trim(void);
 
 /* ------------------------------------------------------------------------
  * Graph construction — replaces utils1.get_adj_mats + distinct

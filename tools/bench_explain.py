@@ -95,6 +95,12 @@ def run(args, shard=None):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         out[name] = {"seconds": dt, "triples_per_s": len(q) / dt, "mean_edges_returned": float(np.mean([len(s) for _, s, _ in res]))}
+        ex.timings = {}
+        t0 = time.perf_counter()
+        ex.explain(q, init, batch_size=args.batch, **kw)
+        out[name]["profiled_run_seconds"] = time.perf_counter() - t0
+        out[name]["phase_seconds"] = {k: round(v, 4) for k, v in ex.timings.items()}
+        ex.timings = None
     if args.cpu_triples and shard is None:
         from oracle import iddgcn_oracle as O
         p = O.ModelParams.from_list([w.astype(np.float32) for w in ws])

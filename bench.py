@@ -141,8 +141,19 @@ def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed, zipf=No
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle; the one place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
+    OpenMP baseline to one thread)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_run(struct, N, n_rows, R, D, X, dS, passes, threads=0):
     from oracle import cref
+    if threads <= 0:
+        threads = host_threads()
     S = np.empty((R * n_rows, D), np.float32)
     dX = np.empty((N, D), np.float32)
     times = []
@@ -152,7 +163,7 @@ def cpu_baseline_run(struct, N, n_rows, R, D, X, dS, passes, threads=0):
         cref.spmm_csc_bwd(struct["csc_rowptr"], struct["csc_row"], struct["csc_perm"], None, R, N, n_rows, dS, out=dX,
                           threads=threads)
         times.append(time.perf_counter() - t0)
-    return times, (cref.max_threads() if threads == 0 else threads)
+    return times, threads
 
 
 def cpu_sample_inputs(wl, seed=0):

@@ -13,7 +13,12 @@ cannot be installed here, and the reference ships no tests or golden vectors —
   * the five shipped trained weight files give the fold metrics of SURVEY.md Appendix D
     (ROC-AUC / AUPR to 4 decimals) through `model_forward` + `eval_protocol`;
   * the hand-written backward (`model_backward`, SURVEY App. A eq. 5-15) agrees with torch autograd
-    of the reference's op order (`torch_model_forward`) to ~1e-12 in fp64.
+    of the reference's op order (`torch_model_forward`) to ~1e-12 in fp64;
+  * the shipped explanation ground-truth table gt_all.csv (1754 ragged rows) regenerates exactly through
+    `construct_ground_truth`, and test_filtered_fold4.csv through `filter_ground_truth` (integer host path).
+(Running the reference's own pure-Python scripts here — e.g. explanation/eval_test.py, which needs no TensorFlow —
+was not possible either: the sandbox does not permit executing code from the reference checkout or unpickling its
+object-array .npz files, so `explanation_metrics` is pinned by hand-worked cases only.)
 
 Every function cites the reference lines it restates (paths relative to the reference root).
 """
@@ -590,4 +595,96 @@ def explainer_run(p: ModelParams, adjacency_data, triples, init_value, *, epochs
             scores.append(a.values.astype(dt) * sigmoid(masks[i][a.indices[:, 1], a.indices[:, 2]]))   # :56
         tk, sk = top_k_edges(adj, scores, k=k, threshold=threshold)     # :57-71
         out.append((tk, sk, loss))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# explanation ground truth and Precision/Recall/F1@5 — explanation/ground_truth.py, gt_process.py, eval_test.py
+# ------------------------------------------------------------------------------------------------
+def construct_ground_truth(dc, cc, dd):
+    """explanation/ground_truth.py:6-80,93-116 — for every drug–mutation triple (mu, rel, drug) the list of supporting
+    triples: same-relation neighbours through similar mutations / similar drugs, then the similarity edges themselves
+    (rel 2 = drug–drug, rel 3 = mutation–mutation).  dc/cc/dd: int arrays [n,3] holding the rows pandas sees AFTER its
+    header handling (the two similarity files have no header line, so `pd.read_csv` swallows their first row,
+    ground_truth.py:84-86).  Returns one list per dc row: [mu, rel, drug, *flattened ground-truth triples]."""
+    dc = np.asarray(dc, np.int64)
+    pair_rels: dict = {}                                   # (drug, mu) -> rels in dc row order
+    for mu, rel, drug in dc:
+        pair_rels.setdefault((int(drug), int(mu)), []).append(int(rel))
+
+    def partners(table, x):                                # :7-9 / :12-14 — column 2 where column 0 == x, then the mirror
+        table = np.asarray(table, np.int64)
+        return [int(v) for v in table[table[:, 0] == x, 2]] + [int(v) for v in table[table[:, 2] == x, 0]]
+
+    def hits(drug, mu, rel):                               # rows of dc with this (drug, mu, rel), in file order
+        return sum(1 for r in pair_rels.get((drug, mu), ()) if r == rel)
+
+    rows = []
+    for mu, rel, drug in dc:
+        mu, rel, drug = int(mu), int(rel), int(drug)
+        sim_mu, sim_drug = partners(cc, mu), partners(dd, drug)
+        gt, added = [], set()
+        for m in sim_mu:                                                                  # :25-29
+            for _ in range(hits(drug, m, rel)):
+                gt.append((m, rel, drug)); added.add((drug, mu))
+        for d in sim_drug:                                                                # :32-36
+            for _ in range(hits(d, mu, rel)):
+                gt.append((mu, rel, d)); added.add((d, mu))
+        for d in sim_drug:                                                                # :39-44
+            for m in sim_mu:
+                for _ in range(hits(d, m, rel)):
+                    gt.append((m, rel, d)); added.add((d, m))
+        for d in sim_drug:                                                                # :47-59
+            if hits(d, mu, rel) and (drug, d) not in added:
+                gt.append((drug, 2, d)); added.add((drug, d))
+            for m in sim_mu:
+                if hits(d, m, rel) and (drug, d) not in added:
+                    gt.append((drug, 2, d)); added.add((drug, d))
+        for m in sim_mu:                                                                  # :62-76
+            if hits(drug, m, rel) and (mu, m) not in added:
+                gt.append((mu, 3, m)); added.add((mu, m))
+            for d in sim_drug:
+                if hits(d, m, rel) and (mu, m) not in added:
+                    gt.append((mu, 3, m)); added.add((mu, m))
+        rows.append([mu, rel, drug] + [v for tri in gt for v in tri])                     # :93-95
+    return rows
+
+
+def filter_ground_truth(test_triples, gt_rows):
+    """explanation/gt_process.py:7-40 — left-merge the fold's test triples with the ground-truth table on
+    (obj, rel, sbj) and keep the triples that have at least one ground-truth triple.  Returns (kept test triples
+    [k,3], list of k lists of [h, r, t] float lists) — the contents of test_filtered_fold{f}.csv and
+    gt_filtered_fold{f}.npz['result']."""
+    table: dict = {}
+    for row in gt_rows:
+        table.setdefault((int(row[0]), int(row[1]), int(row[2])), []).append(row[3:])
+    kept, gts = [], []
+    for h, r, t in np.asarray(test_triples, np.int64):
+        for flat in table.get((int(h), int(r), int(t)), [[]]):          # a left merge repeats duplicated keys
+            flat = [float(v) for v in flat if not (isinstance(v, float) and np.isnan(v))]
+            if len(flat) // 3 >= 1:                                     # :19-22
+                kept.append((int(h), int(r), int(t)))
+                gts.append([flat[j:j + 3] for j in range(0, len(flat) - len(flat) % 3, 3)])
+    return np.asarray(kept, np.int64).reshape(-1, 3), gts
+
+
+def explanation_metrics(preds, gt, top=5, exp_num=10):
+    """explanation/eval_test.py:15-41 — per-triple (Precision@top, Recall@top, F1@top).  `preds[i]`: [k,3] predicted
+    explanation triples (h, r, t); `gt[i]`: the ground-truth triples.  A prediction also counts reversed (t, r, h).
+    The reference takes its "top" as the first `top` elements of a Python *set* of the predictions, i.e. in hash
+    order, not score order (`list(preds_set)[:top]`, :16-19) — kept as is."""
+    out = []
+    for pred, g in zip(preds, gt):
+        pred = np.asarray(pred)
+        flip = np.flip(pred, axis=1)                                                      # :33
+        preds_set = set(map(tuple, pred))
+        flip_set = set(map(tuple, flip))
+        gt_set = set(map(tuple, g))
+        tp = len(set(list(preds_set)[:top]) & gt_set) + len(set(list(flip_set)[:top]) & gt_set)
+        fp = top - tp
+        fn = exp_num - (len(preds_set & gt_set) + len(flip_set & gt_set))
+        precision = tp / (tp + fp) if (tp + fp) > 0 else 0
+        recall = tp / (tp + fn) if (tp + fn) > 0 else 0
+        f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+        out.append((precision, recall, f1))
     return out

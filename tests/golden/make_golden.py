@@ -11,6 +11,10 @@ The GPU box has no /root/reference, so everything a test needs from it is frozen
   h5_sample_fold4.h5      one original .h5 (parser fixture)
   metrics.json            SURVEY Appendix D fold metrics, recomputed here with the oracle in fp64 and fp32
   preds_fold{1,4}.npz     oracle fp64 predictions / pre-sigmoid logits for the eval triples of folds 1 and 4
+  gt_all.npz              the shipped explanation ground-truth table (datasets/explanation_datasets/gt_all.csv, written by
+                          explanation/ground_truth.py) as ragged int16 rows: `flat` + `offsets` — the known answer for
+                          oracle.construct_ground_truth; only the CSV is read (the shipped *.npz files are pickled
+                          object arrays and are not opened)
 """
 import hashlib
 import json
@@ -39,6 +43,13 @@ def main(ref="/root/reference"):
     shutil.copyfile(os.path.join(ex_dir, "test_filtered_fold4.csv"), os.path.join(data_out, "test_filtered_fold4.csv"))
     for fn in os.listdir(data_out):
         os.chmod(os.path.join(data_out, fn), 0o644)
+
+    gt = pd.read_csv(os.path.join(ex_dir, "gt_all.csv")).values                     # float64 with NaN padding
+    rows = [r[~np.isnan(r)] for r in gt]
+    flat = np.concatenate(rows)
+    assert np.array_equal(flat, flat.astype(np.int16)), "ground-truth ids no longer fit int16"
+    np.savez_compressed(os.path.join(HERE, "gt_all.npz"), flat=flat.astype(np.int16),
+                        offsets=np.cumsum([0] + [len(r) for r in rows]).astype(np.int32))
 
     hashes = {}
     for f in range(5):

@@ -126,3 +126,39 @@ def test_fold4_explanation_set_runs_batched(golden_dir):
     ref = O.explainer_run(p, data, test[:3], init.astype(np.float64), epochs=5, lr=1e-3, threshold=0.2,
                           shared_optimizer=False)
     _compare(got[:3], ref, score_tol=5e-5)
+
+
+def test_fold4_explanations_through_precision_recall_f1(golden_dir):
+    """The stage after the explainers (explanation/eval_test.py): GPU explanations of the shipped fold-4 set scored
+    against the ground truth rebuilt from the raw tables.  The product's metric code must agree with the oracle's on
+    the GPU predictions, and for the first triples the predictions themselves (hence their metrics) with the oracle
+    loop's."""
+    import pandas as pd
+    from iddgcn_b200 import explain_eval as E
+    from iddgcn_b200 import get_IDDGCN_Model
+    from iddgcn_b200.explain import Explainer
+    from test_oracle_pins import load_weights
+    d = os.path.join(golden_dir, "data")
+    raw = [pd.read_csv(os.path.join(d, fn)).values for fn in ("triplets_dc.csv", "mu_similar0.97.csv",
+                                                               "drug_similar0.78.csv")]
+    fd = O.fold_pipeline(d)[4]
+    test, gt = E.filter_ground_truth(fd["X_test"].values, E.construct_ground_truth(*raw))
+    assert test.shape == (288, 3)
+    ws = load_weights(golden_dir, 4)
+    data = np.concatenate([fd["X_train"].values, test], 0)
+    m = get_IDDGCN_Model(845, 4, 64, 64, seed=123)
+    m.set_weights(ws)
+    ex = Explainer(m, data)
+    init = np.random.default_rng(24).standard_normal((845, 845)).astype(np.float32)
+    kw = dict(epochs=10, threshold=0.15, structure_target=[0.4, 0.4, 0.1, 0.1])
+    got = ex.explain(test, init, batch_size=288, **kw)
+    preds = [g[0] for g in got]
+    mine = E.explanation_metrics(preds, gt)
+    assert mine == O.explanation_metrics(preds, gt)
+    avg = E.average_metrics(mine)
+    assert 0.0 < avg["Precision@5"] <= 2.0 and 0.0 < avg["Recall@5"] <= 1.0          # explanations do hit the truth
+    p = O.ModelParams.from_list([w.astype(np.float64) for w in ws])
+    ref = O.explainer_run(p, data, test[:3], init.astype(np.float64), lr=1e-3, shared_optimizer=False, **kw)
+    _compare(got[:3], ref, score_tol=5e-5)
+    sne = ex.explaine(test[:4], k=10)
+    assert E.explanation_metrics([s[0] for s in sne], gt[:4]) == O.explanation_metrics([s[0] for s in sne], gt[:4])

@@ -138,3 +138,45 @@ def test_product_fold_pipeline_matches_oracle_and_shipped_files(golden_dir):
         assert np.array_equal(a["X_test"], b["X_test"].values)
         assert np.array_equal(a["neg_train"], b["X_train_neg"][0].astype(np.int64))
         assert np.array_equal(a["neg_test"], b["neg_X_test"].values.astype(np.int64))
+
+
+def test_product_ground_truth_and_metrics_match_oracle(golden_dir, tmp_path):
+    """iddgcn_b200.explain_eval (table look-ups) against the loop restatement in the oracle and the shipped gt_all.csv,
+    then Precision/Recall/F1@5 on synthetic predictions that mix direct hits, reversed hits and misses."""
+    import pandas as pd
+    from iddgcn_b200 import explain_eval as E
+    from oracle import iddgcn_oracle as O
+    d = os.path.join(golden_dir, "data")
+    dc, cc, dd = (pd.read_csv(os.path.join(d, fn)).values
+                  for fn in ("triplets_dc.csv", "mu_similar0.97.csv", "drug_similar0.78.csv"))
+    rows = E.construct_ground_truth(dc, cc, dd)
+    z = np.load(os.path.join(golden_dir, "gt_all.npz"))
+    assert rows == [z["flat"][z["offsets"][i]:z["offsets"][i + 1]].tolist() for i in range(len(z["offsets"]) - 1)]
+    sub = slice(0, 300)                                                         # the loop oracle on a slice (seconds)
+    assert E.construct_ground_truth(dc[sub], cc, dd) == O.construct_ground_truth(dc[sub], cc, dd)
+
+    test_triples = pd.read_csv(os.path.join(d, "test_filtered_fold4.csv")).values
+    extra = np.array([[0, 0, 1], [844, 1, 2]])                                  # triples without ground truth drop out
+    kept, gts = E.filter_ground_truth(np.concatenate([extra[:1], test_triples, extra[1:]]), rows)
+    kept_o, gts_o = O.filter_ground_truth(np.concatenate([extra[:1], test_triples, extra[1:]]), rows)
+    assert np.array_equal(kept, test_triples) and np.array_equal(kept_o, kept) and gts == gts_o
+
+    rng = np.random.default_rng(0)
+    preds = []
+    for g in gts:
+        g = np.asarray(g, np.int64)
+        n = rng.integers(1, 11)
+        fake = rng.integers(0, 845, (n, 3))
+        fake[:, 1] = rng.integers(0, 4, n)
+        take = g[rng.integers(0, len(g), rng.integers(0, 6))]
+        if rng.random() < 0.5:
+            take = take[:, ::-1]
+        p = np.concatenate([take, fake])[:10]
+        preds.append(p[rng.permutation(len(p))])
+    mine, ref = E.explanation_metrics(preds, gts), O.explanation_metrics(preds, gts_o)
+    assert mine == ref and len(mine) == 288
+    avg = E.average_metrics(mine)
+    assert avg["Precision@5"] == pytest.approx(np.mean([m[0] for m in ref]))
+    E.save_ground_truth(tmp_path / "gt.npz", kept, gts)
+    kept2, gts2 = E.load_ground_truth(tmp_path / "gt.npz")
+    assert np.array_equal(kept2, kept) and gts2 == gts

@@ -184,3 +184,45 @@ def test_train_step_descends():
     losses = [O.train_step(p, adj, tri[:50], neg, st, lr=1e-2)[0] for _ in range(6)]
     assert losses[-1] < losses[0]
     assert all(np.array_equal(a, l.relation_weights) for a, l in zip(rw0, p.layers))   # never trained (App. B.4)
+
+
+def _raw_tables(golden_dir):
+    import pandas as pd
+    d = os.path.join(golden_dir, "data")
+    return tuple(pd.read_csv(os.path.join(d, fn)).values                       # ground_truth.py:84-86 (default header)
+                 for fn in ("triplets_dc.csv", "mu_similar0.97.csv", "drug_similar0.78.csv"))
+
+
+def _shipped_gt_all(golden_dir):
+    z = np.load(os.path.join(golden_dir, "gt_all.npz"))
+    flat, off = z["flat"], z["offsets"]
+    return [flat[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+
+def test_ground_truth_table_regenerates_exactly(golden_dir):
+    """explanation/ground_truth.py output == shipped datasets/explanation_datasets/gt_all.csv (all 1754 ragged rows)."""
+    rows = O.construct_ground_truth(*_raw_tables(golden_dir))
+    assert rows == _shipped_gt_all(golden_dir)
+
+
+def test_filtered_explanation_set_regenerates_exactly(folds, golden_dir):
+    """explanation/gt_process.py on fold 4 == shipped test_filtered_fold4.csv (288 triples, same order)."""
+    import pandas as pd
+    kept, gts = O.filter_ground_truth(folds[4]["X_test"].values, _shipped_gt_all(golden_dir))
+    shipped = pd.read_csv(os.path.join(golden_dir, "data", "test_filtered_fold4.csv")).values
+    assert np.array_equal(kept, shipped)
+    assert len(gts) == 288 and all(len(g) >= 1 and all(len(t) == 3 for t in g) for g in gts)
+
+
+def test_explanation_metrics_known_answers():
+    """explanation/eval_test.py:15-41 on hand-worked cases (top=5, exp_num=10)."""
+    gt = [[[1.0, 0.0, 700.0], [2.0, 0.0, 700.0], [700.0, 2.0, 701.0]]]
+    # one direct hit, one reversed hit, one miss: tp=2, fp=3, fn=10-2 -> P=2/5, R=2/10
+    pred = [np.array([[1, 0, 700], [701, 2, 700], [5, 1, 6]])]
+    (p, r, f), = O.explanation_metrics(pred, gt)
+    assert (p, r) == (0.4, 0.2) and f == pytest.approx(2 * 0.4 * 0.2 / 0.6)
+    # nothing right: precision 0, recall 0, f1 0 (the guarded divisions)
+    assert O.explanation_metrics([np.array([[9, 9, 9]])], gt) == [(0.0, 0.0, 0)]
+    # a symmetric triple is counted once directly and once reversed (reference behaviour)
+    (p, r, _), = O.explanation_metrics([np.array([[3, 3, 3]])], [[[3.0, 3.0, 3.0]]])
+    assert (p, r) == (0.4, 0.2)

@@ -661,6 +661,7 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
 
 template <bool USE_PERM>
 static int launch_stream(const StreamArgs& a, int mode, cudaStream_t st) {
+  if (a.nvec <= 4) return launch_stream_mode<4, USE_PERM>(a, mode, st);
   if (a.nvec <= 8) return launch_stream_mode<8, USE_PERM>(a, mode, st);
   if (a.nvec <= 16) return launch_stream_mode<16, USE_PERM>(a, mode, st);
   return launch_stream_mode<32, USE_PERM>(a, mode, st);

@@ -97,7 +97,7 @@ def _vals_for(adj, mode, seed):
 
 
 @pytest.mark.parametrize("kernels", ["v1", "v2"])
-@pytest.mark.parametrize("D", [4, 8, 32, 64, 100, 128, 256, 320])
+@pytest.mark.parametrize("D", [4, 8, 16, 32, 64, 100, 128, 256, 320])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_spmm_family_parity(D, mode, kernels, monkeypatch):
     """Both kernel generations: v1 = one row per lane slice (small graphs, D > 128), v2 = shared-memory index slabs +

@@ -146,6 +146,17 @@ int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const fl
              const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
              bool accumulate, cudaStream_t st) {
   if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
+  // long-M, weight-sized products go to the tensor cores (3xTF32, tc_gemm.cu)
+  if (tc_gemm_eligible(transA, M, N, K, A, lda, B, ldb, C, ldc) && (batch == 1 || ((strideA | strideB | strideC) & 3) == 0) &&
+      tc_gemm_enabled())
+    return gemm_tf32x3(transB, M, N, K, A, lda, strideA, B, strideB, C, ldc, strideC, batch, accumulate, st);
+  return gemm_f32_simt(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, accumulate, st);
+}
+
+int gemm_f32_simt(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                  int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC,
+                  int batch, bool accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
   const int acc = accumulate ? 1 : 0;
   // big tiles only when they are filled and there are enough of them to cover the SMs
   if (N >= 128 && M * batch >= 128 * (int64_t)sm_count())

@@ -14,6 +14,11 @@ int gemm_f32(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const fl
              const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
              bool accumulate, cudaStream_t st);
 
+// the register-tiled fp32 SIMT kernels, never the tensor-core path
+int gemm_f32_simt(bool transA, bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                  int64_t strideA, const float* B, int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC,
+                  int batch, bool accumulate, cudaStream_t st);
+
 // C[b] (+)= A[b]ᵀ · B[b] with a LONG reduction dimension K (A: [K,M], B: [K,N]; M,N small): split-K into
 // a workspace followed by a fixed-order reduction — deterministic, no atomics.
 // workspace must hold gemm_tn_workspace_elems(...) floats.
@@ -21,6 +26,16 @@ size_t gemm_tn_workspace_elems(int64_t M, int64_t N, int64_t K, int batch);
 int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
                        int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
                        bool accumulate, float* workspace, cudaStream_t st);
+
+// ---- tensor-core path (tc_gemm.cu): 3xTF32 on tcgen05 for long-M, weight-sized N = K in {64, 128} ----------------------
+// gemm_f32 takes it by itself when the call is eligible and IDDGCN_GEMM_TF32X3 is not "0".
+bool tc_gemm_enabled();
+bool tc_gemm_eligible(bool transA, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                      int64_t ldb, const float* C, int64_t ldc, int64_t min_rows = 32768);
+int tc_gemm_prepare(cudaStream_t st);   // allocation + attributes; call before capturing a stream that will use it
+int gemm_tf32x3(bool transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA,
+                const float* B, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch, bool accumulate,
+                cudaStream_t st);
 
 // out[b] = in[b]ᵀ for small (weight-sized) row-major matrices [rows, cols]
 int transpose_small(const float* in, float* out, int rows, int cols, int batch, cudaStream_t st);

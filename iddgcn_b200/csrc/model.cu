@@ -284,6 +284,9 @@ static int prepare_train(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_pl
   if (Tt > m->dy_all.n) IDD_CUDA(m->dy_all.ensure(Tt));
   const size_t bs = bce_scratch_elems((int64_t)Tt);
   if (bs > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(bs));
+  // the tensor-core GEMM allocates its weight-split scratch lazily, which a stream capture would forbid
+  if ((m->D == 64 || m->D == 128) && (m->N >= 32768 || 2 * b->T >= 32768) && tc_gemm_enabled())
+    IDD_TRY(tc_gemm_prepare(st));
   *both = b;
   return IDDGCN_OK;
 }
@@ -485,6 +488,22 @@ int iddgcn_adam_step(float* theta, const float* grad, float* m, float* v, int64_
 int iddgcn_relation_transform(const float* S, const float* W, int R, int64_t N, int64_t D, float* Z, void* stream) {
   IDD_CHECK(S && W && Z, IDDGCN_EINVAL, "NULL buffer");
   return gemm_f32(false, false, N, D, D, S, D, N * D, W, D, D * D, Z, D, N * D, R, false, (cudaStream_t)stream);
+}
+
+int iddgcn_dense_transform(const float* A, const float* W, int64_t M, int64_t D, int trans_w, float* C,
+                           int accumulate, int path, void* stream) {
+  IDD_CHECK(A && W && C, IDDGCN_EINVAL, "NULL buffer");
+  IDD_CHECK(M >= 0 && D > 0, IDDGCN_EINVAL, "bad shape M=%lld D=%lld", (long long)M, (long long)D);
+  IDD_CHECK(path >= 0 && path <= 2, IDDGCN_EINVAL, "path must be 0 (automatic), 1 (fp32 SIMT) or 2 (tensor cores)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) return IDDGCN_OK;
+  if (path == 1) return gemm_f32_simt(false, trans_w != 0, M, D, D, A, D, 0, W, D, 0, C, D, 0, 1, accumulate != 0, st);
+  if (path == 2) {
+    IDD_CHECK(tc_gemm_eligible(false, M, D, D, A, D, W, D, C, D, 1), IDDGCN_EINVAL,
+              "the tensor-core path needs D in {64, 128} and 16-byte aligned buffers (D=%lld)", (long long)D);
+    return gemm_tf32x3(trans_w != 0, M, D, D, A, D, 0, W, 0, C, D, 0, 1, accumulate != 0, st);
+  }
+  return gemm_f32(false, trans_w != 0, M, D, D, A, D, 0, W, D, 0, C, D, 0, 1, accumulate != 0, st);
 }
 
 int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb, const float* Hin, const float* Tin, const float* Z,

@@ -169,6 +169,14 @@ int iddgcn_plan_destroy(iddgcn_plan_t* p);
  *   per-relation transform hoisted from the T gathered rows (IDDGCN.py:76-77)
  *   to the N aggregated rows; same dot products, same values.
  *   _bwd: dW[r] += S[r]ᵀ·dZ[r];  dS[r] (+)= dZ[r]·W[r]ᵀ.
+ * iddgcn_dense_transform: C[M,D] (+)= A[M,D]·W (trans_w = 0; W is [D,D]
+ *   row-major — tf.matmul(head_e, self_kernel) / tf.matmul(update,
+ *   relation_kernel[i]), IDDGCN.py:62-63,76-77) or A·Wᵀ (trans_w = 1, the data
+ *   gradient of that product).  path 0 = automatic: fp32 SIMT, or — when
+ *   M >= 32768 and D is 64 or 128 — the tensor cores (tcgen05, 3xTF32 split,
+ *   ~2^-21 relative per product; IDDGCN_GEMM_TF32X3=0 turns that off);
+ *   1 = always fp32 SIMT; 2 = always tensor cores (D in {64,128}).  The layer
+ *   and model entry points use the automatic choice.
  * iddgcn_layer_fwd: for every triple k
  *     alpha = softmax(Hin[k]·W_alpha + b_alpha); gate_i = sigmoid(alpha_i)   (:66,:75)
  *     P_H = Hin[k]·W_self + Σ_i gate_i · Z_i[head_k]                          (:62,:76)
@@ -195,6 +203,8 @@ int iddgcn_relation_transform(const float* S, const float* W, int R, int64_t N, 
                               float* Z, void* stream);
 int iddgcn_relation_transform_bwd(const float* S, const float* W, const float* dZ, int R, int64_t N, int64_t D,
                                   float* dW, float* dS, int accumulate_dS, void* stream);
+int iddgcn_dense_transform(const float* A, const float* W, int64_t M, int64_t D, int trans_w,
+                           float* C, int accumulate, int path, void* stream);
 int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb,
                      const float* Hin, const float* Tin, const float* Z,
                      const float* W_self, const float* W_alpha, const float* b_alpha,

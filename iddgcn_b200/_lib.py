@@ -44,6 +44,7 @@ _SIGNATURES = {
     "iddgcn_relation_transform": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp]),
     "iddgcn_relation_transform_bwd": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]),
     "iddgcn_dense_transform": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int, vp, C.c_int, C.c_int, vp]),
+    "iddgcn_dense_transform_grad": (C.c_int, [vp, vp, C.c_int64, C.c_int64, vp, C.c_int, C.c_int, vp]),
     "iddgcn_layer_fwd": (C.c_int, [vp] * 8 + [C.c_int64, vp, vp, vp, vp]),
     "iddgcn_layer_bwd": (C.c_int, [vp] * 7 + [C.c_int64, vp, vp, vp, C.c_int, vp, vp, vp, vp]),
     "iddgcn_segment_scatter": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int, vp]),

@@ -186,12 +186,38 @@ static void splitk_shape(int64_t M, int64_t N, int64_t K, int batch, int* splits
 size_t gemm_tn_workspace_elems(int64_t M, int64_t N, int64_t K, int batch) {
   int splits; int64_t chunk;
   splitk_shape(M, N, K, batch, &splits, &chunk);
+  if (M == N && (M == 64 || M == 128) && tc_gemm_tn_splits(K) > splits) splits = tc_gemm_tn_splits(K);   // either path fits
   return (size_t)splits * (size_t)M * (size_t)N * (size_t)batch;
 }
 
 int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
                        int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
                        bool accumulate, float* workspace, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
+  const int64_t MN = M * N;
+  // long reductions into a weight-sized square go to the tensor cores (3xTF32, tc_gemm.cu), same workspace + reduction
+  if (tc_gemm_tn_eligible(M, N, K, A, lda, B, ldb) && (batch == 1 || ((strideA | strideB) & 3) == 0) && tc_gemm_enabled())
+    return gemm_tn_tc(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, accumulate, workspace, st);
+  return gemm_tn_splitk_simt(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, accumulate, workspace, st);
+}
+
+int gemm_tn_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
+               int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch, bool accumulate,
+               float* workspace, cudaStream_t st) {
+  const int64_t MN = M * N;
+  const int splits = tc_gemm_tn_splits(K);
+  for (int b = 0; b < batch; ++b)
+    IDD_TRY(gemm_tn_tf32x3_partials(M, K, A + (int64_t)b * strideA, lda, B + (int64_t)b * strideB, ldb,
+                                    workspace + (int64_t)b * splits * MN, st));
+  dim3 rgrid((unsigned)((MN + 31) / 32), (unsigned)batch);
+  splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(workspace, splits, MN, N, C, ldc, strideC, accumulate ? 1 : 0);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
+int gemm_tn_splitk_simt(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
+                        int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
+                        bool accumulate, float* workspace, cudaStream_t st) {
   if (M <= 0 || N <= 0 || batch <= 0) return IDDGCN_OK;
   int splits; int64_t chunk;
   splitk_shape(M, N, K, batch, &splits, &chunk);

@@ -37,6 +37,21 @@ int gemm_tf32x3(bool transB, int64_t M, int64_t N, int64_t K, const float* A, in
                 const float* B, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch, bool accumulate,
                 cudaStream_t st);
 
+// weight-gradient product on the tensor cores: partial sums over tc_gemm_tn_splits(K) row ranges into ws[s][M][N]
+int tc_gemm_tn_splits(int64_t rows);
+bool tc_gemm_tn_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                         int64_t min_rows = 32768);
+int gemm_tn_tf32x3_partials(int64_t M, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* ws,
+                            cudaStream_t st);
+
+// the two implementations behind gemm_tn_splitk_f32 (same workspace contract)
+int gemm_tn_splitk_simt(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
+                        int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch,
+                        bool accumulate, float* workspace, cudaStream_t st);
+int gemm_tn_tc(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, int64_t strideA, const float* B,
+               int64_t ldb, int64_t strideB, float* C, int64_t ldc, int64_t strideC, int batch, bool accumulate,
+               float* workspace, cudaStream_t st);
+
 // out[b] = in[b]ᵀ for small (weight-sized) row-major matrices [rows, cols]
 int transpose_small(const float* in, float* out, int rows, int cols, int batch, cudaStream_t st);
 

@@ -506,6 +506,28 @@ int iddgcn_dense_transform(const float* A, const float* W, int64_t M, int64_t D,
   return gemm_f32(false, trans_w != 0, M, D, D, A, D, 0, W, D, 0, C, D, 0, 1, accumulate != 0, st);
 }
 
+int iddgcn_dense_transform_grad(const float* A, const float* dC, int64_t M, int64_t D, float* dW, int accumulate,
+                                int path, void* stream) {
+  IDD_CHECK(A && dC && dW, IDDGCN_EINVAL, "NULL buffer");
+  IDD_CHECK(M >= 0 && D > 0, IDDGCN_EINVAL, "bad shape M=%lld D=%lld", (long long)M, (long long)D);
+  IDD_CHECK(path >= 0 && path <= 2, IDDGCN_EINVAL, "path must be 0 (automatic), 1 (fp32 SIMT) or 2 (tensor cores)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf<float> ws;
+  IDD_CUDA(ws.ensure(gemm_tn_workspace_elems(D, D, M, 1)));
+  int rc;
+  if (path == 1) {
+    rc = gemm_tn_splitk_simt(D, D, M, A, D, 0, dC, D, 0, dW, D, 0, 1, accumulate != 0, ws.p, st);
+  } else if (path == 2) {
+    IDD_CHECK(tc_gemm_tn_eligible(D, D, M, A, D, dC, D, 1), IDDGCN_EINVAL,
+              "the tensor-core path needs D in {64, 128}, M >= 1 and 16-byte aligned buffers (D=%lld)", (long long)D);
+    rc = gemm_tn_tc(D, D, M, A, D, 0, dC, D, 0, dW, D, 0, 1, accumulate != 0, ws.p, st);
+  } else {
+    rc = gemm_tn_splitk_f32(D, D, M, A, D, 0, dC, D, 0, dW, D, 0, 1, accumulate != 0, ws.p, st);
+  }
+  IDD_CUDA(cudaStreamSynchronize(st));   // the workspace is released on return
+  return rc;
+}
+
 int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb, const float* Hin, const float* Tin, const float* Z,
                      const float* W_self, const float* W_alpha, const float* b_alpha, int64_t D, float* Hout,
                      float* Tout, float* alpha_out, void* stream) {

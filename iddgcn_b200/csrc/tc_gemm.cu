@@ -365,7 +365,8 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // fp32 [rows, cols] row-major with leading dimension ld (floats); box = 32 columns × box_rows rows, SWIZZLE_128B
-int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_tiled_fn();
   IDD_CHECK(enc != nullptr, IDDGCN_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -373,7 +374,7 @@ int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int
   const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IDD_CHECK(r == CUDA_SUCCESS, IDDGCN_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return IDDGCN_OK;
@@ -428,6 +429,258 @@ int split_ws(cudaStream_t st, float** out) {
   return IDDGCN_OK;
 }
 
+
+// =====================================================================================================================
+// Weight-gradient product  C[Mo,No] = Σ_rows A[row, :Mo]ᵀ · B[row, :No]   (dW = Sᵀ·dZ, dW_self = Hᵀ·dP): both operands
+// stream, the reduction runs over millions of rows, the output is weight-sized (Mo = No ∈ {64, 128}).
+//
+// Each CTA owns a contiguous range of rows.  Per k-block of 32 rows the producer lands A and B as 32-float-wide column
+// atoms ([32 rows × 128 B], SWIZZLE_128B_ATOM_32B) — which is exactly the MN-major canonical layout of the tensor core: both
+// operands are consumed "transposed" without any data movement.  The splitter turns both into hi/lo in place, the MMA
+// thread issues 4 × 3 tcgen05.mma (128 × No × 8).  Tensor-core accumulation is not round-to-nearest, so the TMEM
+// accumulator is only trusted for TN_FLUSH k-blocks (256 rows): the epilogue warps then pull it (tcgen05.ld) and add it
+// to a register-resident fp32 total while the MMAs continue into the second TMEM buffer.  At the end every CTA writes
+// its 128 × No total to the split-K workspace; dense.cu's fixed-order reduction finishes the sum (deterministic).
+// For Mo = 64 the upper half of the A operand is shared memory zeroed once (the tensor core's M is 128).
+// =====================================================================================================================
+constexpr int TN_FLUSH = 8;            // k-blocks accumulated inside TMEM between two flushes
+constexpr int TN_PREFETCH = 4;         // k-blocks of L2 prefetch distance
+constexpr int TN_THREADS = 320;        // warps 0-3 epilogue, 4-7 splitter, 8 producer, 9 MMA
+constexpr int TN_ATOM = 32 * 128;      // one column atom: 32 rows × 128 bytes
+
+// MN-major tf32 operands have exactly one legal shared-memory layout: 128-byte rows whose 32-BYTE chunks are swizzled
+// with (row % 4) (UMMA layout type 1, "128B swizzle, 32B atom" — what TMA's SWIZZLE_128B_ATOM_32B writes).  The swizzle
+// atom is 4 rows × 128 bytes: leading byte offset = distance between 32-float column atoms (4096), stride byte offset =
+// distance between 4-row groups (512); one MMA (K = 8) spans two groups.
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(TN_ATOM >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+__host__ __device__ constexpr uint32_t tf32_idesc_mn(int M, int N) { return tf32_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+template <int D_, int STAGES>
+struct TnSmem {
+  static constexpr int ATOMS = D_ / 32;                                // real column atoms of A and of B
+  static constexpr int A_SLAB = 4 * TN_ATOM;                           // the A operand always spans M = 128
+  static constexpr int B_SLAB = ATOMS * TN_ATOM;
+  static constexpr int STAGE = 2 * A_SLAB + 2 * B_SLAB;                // A hi, A lo, B hi, B lo
+  static constexpr int BAR_OFF = STAGES * STAGE;
+  static constexpr int NBARS = 3 * STAGES + 4;
+  static constexpr int BYTES = BAR_OFF + NBARS * 8 + 16;
+  static constexpr int DYN_BYTES = BYTES + 1024;
+  static constexpr uint32_t TX = (uint32_t)(2 * ATOMS * TN_ATOM);      // bytes one k-block brings in
+};
+
+template <int D_, int STAGES>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+    tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      float* __restrict__ ws, int64_t rows, int kb_per_cta) {
+  using L = TnSmem<D_, STAGES>;
+  constexpr int ATOMS = L::ATOMS;
+  constexpr int TMEM_COLS = 2 * D_;
+  extern __shared__ uint8_t tc_smem_raw[];
+  const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = tc_smem_raw + (base - smem_u32(tc_smem_raw));
+  const uint32_t sBar = base + L::BAR_OFF;
+  auto bar_full = [&](int s) { return sBar + 8u * s; };
+  auto bar_ready = [&](int s) { return sBar + 8u * (STAGES + s); };
+  auto bar_empty = [&](int s) { return sBar + 8u * (2 * STAGES + s); };
+  auto bar_tfull = [&](int a) { return sBar + 8u * (3 * STAGES + a); };
+  auto bar_tempty = [&](int a) { return sBar + 8u * (3 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::BAR_OFF + L::NBARS * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t total_kb = (rows + 31) / 32;
+  const int64_t kb0 = (int64_t)blockIdx.x * kb_per_cta;
+  const int64_t kb1 = kb0 + kb_per_cta < total_kb ? kb0 + kb_per_cta : total_kb;
+  const int nkb = kb1 > kb0 ? (int)(kb1 - kb0) : 0;
+  const int ngroups = (nkb + TN_FLUSH - 1) / TN_FLUSH;
+
+  if (ATOMS < 4) {  // rows Mo..127 of the A operand are never loaded: zero them once (hi and lo, every stage)
+    for (int s = 0; s < STAGES; ++s)
+      for (int half = 0; half < 2; ++half) {
+        float4* z = reinterpret_cast<float4*>(base_ptr + (size_t)s * L::STAGE + half * L::A_SLAB + ATOMS * TN_ATOM);
+        for (int i = threadIdx.x; i < (4 - ATOMS) * TN_ATOM / 16; i += TN_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    fence_proxy_async();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull(a), 1);
+      mbar_init(bar_tempty(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<TMEM_COLS>(smem_u32((const void*)tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1u;
+        const int row = (int)((kb0 + i) * 32);
+        if (i + TN_PREFETCH < nkb) {
+#pragma unroll
+          for (int c = 0; c < ATOMS; ++c) {
+            tma_prefetch_l2_2d(&map_a, c * 32, row + TN_PREFETCH * 32);
+            tma_prefetch_l2_2d(&map_b, c * 32, row + TN_PREFETCH * 32);
+          }
+        }
+        mbar_wait(bar_empty(s), ph ^ 1u);
+        mbar_expect_tx(bar_full(s), L::TX);
+        const uint32_t st = base + (uint32_t)s * L::STAGE;
+#pragma unroll
+        for (int c = 0; c < ATOMS; ++c) {
+          tma_load_2d(st + c * TN_ATOM, &map_a, bar_full(s), c * 32, row);
+          tma_load_2d(st + 2 * L::A_SLAB + c * TN_ATOM, &map_b, bar_full(s), c * 32, row);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = tf32_idesc_mn(128, D_);
+      int i = 0;
+      for (int gidx = 0; gidx < ngroups; ++gidx) {
+        const int a = gidx & 1;
+        const uint32_t aph = (uint32_t)(gidx >> 1) & 1u;
+        mbar_wait(bar_tempty(a), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * D_);
+        const int gend = (gidx + 1) * TN_FLUSH < nkb ? (gidx + 1) * TN_FLUSH : nkb;
+        for (bool first = true; i < gend; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1u;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
+          const uint32_t st = base + (uint32_t)s * L::STAGE;
+          const uint64_t a_hi = mnmajor_sw128_desc(st), a_lo = mnmajor_sw128_desc(st + L::A_SLAB);
+          const uint64_t b_hi = mnmajor_sw128_desc(st + 2 * L::A_SLAB);
+          const uint64_t b_lo = mnmajor_sw128_desc(st + 2 * L::A_SLAB + L::B_SLAB);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                       // 8 rows = one 1024-byte group per MMA
+            const uint64_t adv = (uint64_t)(k * 64);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, first ? 0u : 1u);
+            first = false;
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(bar_empty(s));
+        }
+        umma_commit(bar_tfull(a));
+      }
+    }
+  } else if (warp < 4) {
+    // ===== epilogue: fp32 running total in registers, one output row per thread =====
+    float total[D_];
+#pragma unroll
+    for (int j = 0; j < D_; ++j) total[j] = 0.f;
+    for (int gidx = 0; gidx < ngroups; ++gidx) {
+      const int a = gidx & 1;
+      const uint32_t aph = (uint32_t)(gidx >> 1) & 1u;
+      mbar_wait(bar_tfull(a), aph);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < D_; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * D_ + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) total[c0 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(a));
+    }
+    const int row = warp * 32 + lane;
+    if (row < D_) {
+      float* out = ws + ((size_t)blockIdx.x * D_ + row) * D_;
+#pragma unroll
+      for (int j = 0; j < D_; j += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(total[j + e]);
+        st_global_v8(out + j, v);
+      }
+    }
+  } else if (warp < 8) {
+    // ===== splitter: both operands of the landed k-block -> hi in place, lo beside =====
+    const int t = threadIdx.x - 128;                            // 0..127
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1u;
+      mbar_wait(bar_full(s), ph);
+      uint8_t* st = base_ptr + (size_t)s * L::STAGE;
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        float4* hi = reinterpret_cast<float4*>(st + (op ? 2 * L::A_SLAB : 0));
+        float4* lo = reinterpret_cast<float4*>(st + (op ? 2 * L::A_SLAB + L::B_SLAB : L::A_SLAB));
+#pragma unroll
+        for (int q = 0; q < ATOMS * TN_ATOM / 16 / 128; ++q) {
+          const int o = q * 128 + t;
+          const float4 x = hi[o];
+          const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+          hi[o] = h;
+          lo[o] = make_float4(tf32_round(x.x - h.x), tf32_round(x.y - h.y), tf32_round(x.z - h.z),
+                              tf32_round(x.w - h.w));
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_ready(s));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// fp32 [rows, cols] row-major, ld floats between rows; box = 32 columns × 32 rows (one column atom), 32-byte swizzle atom
+int make_map_atom(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  return make_map(map, ptr, rows, cols, ld, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+template <int D_, int STAGES>
+int configure_tn() {
+  using L = TnSmem<D_, STAGES>;
+  static_assert(L::DYN_BYTES <= 227 * 1024, "shared-memory budget exceeded");
+  static bool configured[64] = {};
+  int dev = 0;
+  IDD_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !configured[dev]) {
+    IDD_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<D_, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::DYN_BYTES));
+    if (dev < 64) configured[dev] = true;
+  }
+  return IDDGCN_OK;
+}
+
+template <int D_, int STAGES>
+int launch_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t rows, float* ws, int grid,
+              int kb_per_cta, cudaStream_t st) {
+  using L = TnSmem<D_, STAGES>;
+  IDD_TRY((configure_tn<D_, STAGES>()));
+  CUtensorMap ma, mb;
+  IDD_TRY(make_map_atom(&ma, A, rows, D_, lda));
+  IDD_TRY(make_map_atom(&mb, B, rows, D_, ldb));
+  tc_gemm_tn_kernel<D_, STAGES><<<(unsigned)grid, TN_THREADS, L::DYN_BYTES, st>>>(ma, mb, ws, rows, kb_per_cta);
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
 }  // namespace
 
 // Everything that may not happen inside a stream capture (allocation, function attributes): call once per stream
@@ -437,8 +690,35 @@ int tc_gemm_prepare(cudaStream_t st) {
   IDD_TRY(split_ws(st, &ws));
   IDD_TRY((configure_tc<128, 128, 3>()));
   IDD_TRY((configure_tc<64, 64, 5>()));
+  IDD_TRY((configure_tn<128, 3>()));
+  IDD_TRY((configure_tn<64, 4>()));
   IDD_CHECK(encode_tiled_fn() != nullptr, IDDGCN_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   return IDDGCN_OK;
+}
+
+// number of row ranges (= partial sums written to the workspace) the weight-gradient kernel uses for `rows` rows
+int tc_gemm_tn_splits(int64_t rows) {
+  const int64_t total_kb = (rows + 31) / 32;
+  const int64_t want = total_kb < sm_count() ? total_kb : sm_count();
+  const int64_t per = (total_kb + want - 1) / want;
+  return (int)((total_kb + per - 1) / per);
+}
+
+bool tc_gemm_tn_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+                         int64_t min_rows) {
+  if (M != N || (M != 64 && M != 128) || K < min_rows || K >= ((int64_t)1 << 31) - 64) return false;
+  if ((lda % 4) != 0 || (ldb % 4) != 0 || lda < M || ldb < N) return false;
+  return ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15u) == 0;
+}
+
+// ws[s][M][N] (s < tc_gemm_tn_splits(K)) = partial sums of A[K,M]ᵀ·B[K,N]; the caller reduces them in fixed order
+int gemm_tn_tf32x3_partials(int64_t M, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb, float* ws,
+                            cudaStream_t st) {
+  const int grid = tc_gemm_tn_splits(K);
+  const int64_t total_kb = (K + 31) / 32;
+  const int per = (int)((total_kb + grid - 1) / grid);
+  if (M == 128) return launch_tn<128, 3>(A, lda, B, ldb, K, ws, grid, per, st);
+  return launch_tn<64, 4>(A, lda, B, ldb, K, ws, grid, per, st);
 }
 
 bool tc_gemm_enabled() {

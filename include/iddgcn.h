@@ -177,6 +177,12 @@ int iddgcn_plan_destroy(iddgcn_plan_t* p);
  *   ~2^-21 relative per product; IDDGCN_GEMM_TF32X3=0 turns that off);
  *   1 = always fp32 SIMT; 2 = always tensor cores (D in {64,128}).  The layer
  *   and model entry points use the automatic choice.
+ * iddgcn_dense_transform_grad: dW[D,D] (+)= Aᵀ[D,M]·dC[M,D], the weight gradient
+ *   of the product above (what tape.gradient emits for tf.matmul, IDDGCN.py:172);
+ *   a reduction over M rows summed in a fixed order (deterministic).  Same
+ *   `path` values; the tensor-core path keeps the accumulation inside the
+ *   tensor core to 256 rows at a time and sums those pieces in fp32 registers.
+ *   Synchronises the stream before returning (internal scratch).
  * iddgcn_layer_fwd: for every triple k
  *     alpha = softmax(Hin[k]·W_alpha + b_alpha); gate_i = sigmoid(alpha_i)   (:66,:75)
  *     P_H = Hin[k]·W_self + Σ_i gate_i · Z_i[head_k]                          (:62,:76)
@@ -205,6 +211,8 @@ int iddgcn_relation_transform_bwd(const float* S, const float* W, const float* d
                                   float* dW, float* dS, int accumulate_dS, void* stream);
 int iddgcn_dense_transform(const float* A, const float* W, int64_t M, int64_t D, int trans_w,
                            float* C, int accumulate, int path, void* stream);
+int iddgcn_dense_transform_grad(const float* A, const float* dC, int64_t M, int64_t D, float* dW,
+                                int accumulate, int path, void* stream);
 int iddgcn_layer_fwd(const iddgcn_plan_t* p, const float* emb,
                      const float* Hin, const float* Tin, const float* Z,
                      const float* W_self, const float* W_alpha, const float* b_alpha,

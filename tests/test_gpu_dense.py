@@ -103,3 +103,64 @@ def test_many_tiles_per_cta_and_determinism():
     b = _transform(A, W, 1, C0, path=2)
     assert np.array_equal(a, b)
     assert _scaled_err(a, A, W, 1, C0) < TC_TOL
+
+
+# ---- weight gradient dW (+)= Aᵀ·dC ------------------------------------------------------------------------------------
+def _grad(A, dC, W0, path):
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    a = torch.as_tensor(A, device=dev).contiguous()
+    d = torch.as_tensor(dC, device=dev).contiguous()
+    D = A.shape[1]
+    w = torch.as_tensor(W0, device=dev).clone() if W0 is not None else torch.full((D, D), float("nan"), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.iddgcn_dense_transform_grad(_lib.ptr(a), _lib.ptr(d), A.shape[0], D, _lib.ptr(w),
+                                               int(W0 is not None), path, C.c_void_p(st)))
+    torch.cuda.synchronize()
+    return w.cpu().numpy()
+
+
+def _grad_err(got, A, dC, W0):
+    ref = A.astype(np.float64).T @ dC.astype(np.float64) + (W0.astype(np.float64) if W0 is not None else 0.0)
+    scale = np.abs(A).astype(np.float64).T @ np.abs(dC).astype(np.float64) + (np.abs(W0) if W0 is not None else 0.0)
+    return float(np.max(np.abs(got - ref) / scale))
+
+
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("M", [1, 31, 32, 33, 255, 256, 257, 5000, 300000])
+def test_tensor_core_weight_gradient_matches_fp64(D, M):
+    """Row counts around the 32-row k-block and the 256-row TMEM flush, fewer k-blocks than SMs, and a long reduction."""
+    rng = np.random.default_rng(M + D)
+    A = rng.standard_normal((M, D)).astype(np.float32)
+    dC = rng.standard_normal((M, D)).astype(np.float32)
+    if M == 5000:
+        A *= np.exp2(rng.integers(-6, 7, (M, D))).astype(np.float32)
+    W0 = rng.standard_normal((D, D)).astype(np.float32)
+    for acc in (None, W0):
+        got = _grad(A, dC, acc, path=2)
+        assert np.isfinite(got).all()
+        assert _grad_err(got, A, dC, acc) < TC_TOL
+        assert _grad_err(_grad(A, dC, acc, path=1), A, dC, acc) < SIMT_TOL
+
+
+def test_weight_gradient_is_exact_on_split_sensitive_values_and_deterministic():
+    """Aᵀ·dC with dC = [I; 0; ...] picks single rows of A: exact only if hi and lo both arrive, transposed correctly."""
+    D, M = 128, 4096
+    rng = np.random.default_rng(0)
+    A = (1.0 + rng.integers(0, 2 ** 20, (M, D)) * 2.0 ** -20).astype(np.float32)        # full 21-bit mantissas
+    dC = np.zeros((M, D), np.float32)
+    rows = rng.permutation(M)[:D]
+    dC[rows, np.arange(D)] = 1.0                                                          # dW[i, j] = A[rows[j], i]
+    got = _grad(A, dC, None, path=2)
+    assert np.array_equal(got, A[rows].T)
+    assert np.array_equal(got, _grad(A, dC, None, path=2))
+
+
+def test_weight_gradient_automatic_choice(monkeypatch):
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((40000, 128)).astype(np.float32)
+    dC = rng.standard_normal((40000, 128)).astype(np.float32)
+    assert np.array_equal(_grad(A, dC, None, 0), _grad(A, dC, None, 2))
+    assert np.array_equal(_grad(A[:1000], dC[:1000], None, 0), _grad(A[:1000], dC[:1000], None, 1))
+    monkeypatch.setenv("IDDGCN_GEMM_TF32X3", "0")
+    assert np.array_equal(_grad(A, dC, None, 0), _grad(A, dC, None, 1))

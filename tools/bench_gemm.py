@@ -47,6 +47,22 @@ def main():
                 out[f"D{D}_{name}_{'accumulate' if acc else 'overwrite'}"] = {
                     "ms": round(ms, 4), "TFLOPs": round(2.0 * M * D * D / ms / 1e9, 2),
                     "GBps": round((2 + acc) * M * D * 4 / ms / 1e6, 1)}
+        dw = torch.empty(D, D, device=dev)
+        for name, path in (("simt_fp32", 1), ("tcgen05_tf32x3", 2)):
+            call = lambda: _lib.check(lib.iddgcn_dense_transform_grad(_lib.ptr(a), _lib.ptr(c), M, D, _lib.ptr(dw), 0, path,
+                                                                      C.c_void_p(st)))
+            for _ in range(3):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.iters):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.iters
+            out[f"D{D}_grad_{name}"] = {"ms": round(ms, 4), "TFLOPs": round(2.0 * M * D * D / ms / 1e9, 2),
+                                        "GBps": round(2 * M * D * 4 / ms / 1e6, 1)}
         ref = (a[:4096].double() @ w.double()).float()
         _lib.check(lib.iddgcn_dense_transform(_lib.ptr(a), _lib.ptr(w), 4096, D, 0, _lib.ptr(c), 0, 2, C.c_void_p(st)))
         torch.cuda.synchronize()

@@ -164,6 +164,74 @@ int gemm_f32_simt(bool transA, bool transB, int64_t M, int64_t N, int64_t K, con
   return gemm_launch<4, 4>(transA, transB, M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, acc, st);
 }
 
+// ---- tall-skinny reduction: C[M,N] (+)= A[K,M]ᵀ · B[K,N] with N <= 8 (the gate gradient dW_alpha = Hᵀ·dz, N = R) -------
+// A 64x64 register tile wastes 7/8 of its work on N = 2..8, and the product is a weighted column sum of A anyway: every
+// warp streams whole rows of A (lane = one float4 of columns, coalesced), multiplies by the row's N weights (broadcast
+// loads) and keeps N x 4 running sums in registers.  HBM-bound on A.  Warps of a block are combined in a fixed order and
+// the blocks by splitk_reduce_kernel: deterministic.
+constexpr int SK_WARPS = 8;
+constexpr int SK_NMAX = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(SK_WARPS * 32)
+    tn_skinny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K, int M,
+                     int N, int64_t rows_per_block, float* __restrict__ ws) {
+  extern __shared__ float sk_smem[];                         // [SK_WARPS][M][N]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = M >> 2;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < K ? r0 + rows_per_block : K;
+  float acc[NV][SK_NMAX][4];
+#pragma unroll
+  for (int c = 0; c < NV; ++c)
+#pragma unroll
+    for (int n = 0; n < SK_NMAX; ++n) acc[c][n][0] = acc[c][n][1] = acc[c][n][2] = acc[c][n][3] = 0.f;
+  for (int64_t r = r0 + warp; r < r1; r += SK_WARPS) {
+    float b[SK_NMAX];
+#pragma unroll
+    for (int n = 0; n < SK_NMAX; ++n) b[n] = n < N ? __ldg(B + r * ldb + n) : 0.f;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int v = lane + c * 32;
+      if (v < nvec) {
+        const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(A + r * lda) + v);
+#pragma unroll
+        for (int n = 0; n < SK_NMAX; ++n) {
+          acc[c][n][0] += a.x * b[n]; acc[c][n][1] += a.y * b[n];
+          acc[c][n][2] += a.z * b[n]; acc[c][n][3] += a.w * b[n];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int v = lane + c * 32;
+    if (v < nvec)
+#pragma unroll
+      for (int n = 0; n < SK_NMAX; ++n)
+        if (n < N)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sk_smem[((size_t)warp * M + v * 4 + e) * N + n] = acc[c][n][e];
+  }
+  __syncthreads();
+  const int MN = M * N;
+  for (int i = threadIdx.x; i < MN; i += SK_WARPS * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) t += sk_smem[(size_t)w * MN + i];
+    ws[(size_t)blockIdx.x * MN + i] = t;
+  }
+}
+
+static int skinny_blocks(int64_t K) {
+  const int64_t want = 2 * (int64_t)sm_count(), by_k = (K + 255) / 256;
+  return (int)(want < by_k ? want : (by_k < 1 ? 1 : by_k));
+}
+static bool skinny_eligible(int64_t M, int64_t N, int64_t K, const float* A, int64_t lda) {
+  return N <= SK_NMAX && M <= 512 && (M % 4) == 0 && (lda % 4) == 0 && K >= 1024 &&
+         (size_t)SK_WARPS * M * N * sizeof(float) <= 48 * 1024 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0;
+}
+
 // split-K tile edge: 128 when both output dimensions fill it (A and B are then read exactly once), else 64
 static inline int splitk_tile(int64_t M, int64_t N) { return (M >= 128 && N >= 128) ? 128 : 64; }
 
@@ -187,6 +255,7 @@ size_t gemm_tn_workspace_elems(int64_t M, int64_t N, int64_t K, int batch) {
   int splits; int64_t chunk;
   splitk_shape(M, N, K, batch, &splits, &chunk);
   if (M == N && (M == 64 || M == 128) && tc_gemm_tn_splits(K) > splits) splits = tc_gemm_tn_splits(K);   // either path fits
+  if (N <= SK_NMAX && skinny_blocks(K) > splits) splits = skinny_blocks(K);
   return (size_t)splits * (size_t)M * (size_t)N * (size_t)batch;
 }
 
@@ -198,6 +267,24 @@ int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
   // long reductions into a weight-sized square go to the tensor cores (3xTF32, tc_gemm.cu), same workspace + reduction
   if (tc_gemm_tn_eligible(M, N, K, A, lda, B, ldb) && (batch == 1 || ((strideA | strideB) & 3) == 0) && tc_gemm_enabled())
     return gemm_tn_tc(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, accumulate, workspace, st);
+  if (skinny_eligible(M, N, K, A, lda) && (batch == 1 || (strideA & 3) == 0)) {
+    const int blocks = skinny_blocks(K);
+    const int64_t per = (K + blocks - 1) / blocks;
+    const size_t smem = (size_t)SK_WARPS * MN * sizeof(float);
+    for (int b = 0; b < batch; ++b) {
+      const float* Ab = A + (int64_t)b * strideA;
+      const float* Bb = B + (int64_t)b * strideB;
+      float* wsb = workspace + (int64_t)b * blocks * MN;
+      if (M <= 128) tn_skinny_kernel<1><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
+      else if (M <= 256) tn_skinny_kernel<2><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
+      else tn_skinny_kernel<4><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
+      IDD_LAUNCH_CHECK();
+    }
+    dim3 rgrid((unsigned)((MN + 31) / 32), (unsigned)batch);
+    splitk_reduce_kernel<<<rgrid, 256, 0, st>>>(workspace, blocks, MN, N, C, ldc, strideC, accumulate ? 1 : 0);
+    IDD_LAUNCH_CHECK();
+    return IDDGCN_OK;
+  }
   return gemm_tn_splitk_simt(M, N, K, A, lda, strideA, B, ldb, strideB, C, ldc, strideC, batch, accumulate, workspace, st);
 }
 

@@ -222,18 +222,28 @@ int layer_bwd_pre(const iddgcn_plan* p, const float* HT_out, const float* alpha,
 __global__ void __launch_bounds__(256) layer_bwd_post_kernel(const float* __restrict__ dz,
                                                              const float* __restrict__ W_alpha, int64_t T, int D,
                                                              int R, float* __restrict__ dHin) {
+  // one thread per float4 of a row; same per-element arithmetic and order as a scalar loop over r
+  const int nvec = D >> 2;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= T * D) return;
-  const int64_t k = i / D;
-  const int d = (int)(i % D);
-  float acc = dHin[i];
-  for (int r = 0; r < R; ++r) acc = fmaf(dz[k * R + r], __ldg(W_alpha + d * R + r), acc);
-  dHin[i] = acc;
+  if (i >= T * nvec) return;
+  const int64_t k = i / nvec;
+  const int d = (int)(i - k * nvec) * 4;
+  float4* p = reinterpret_cast<float4*>(dHin) + i;
+  float4 acc = *p;
+  for (int r = 0; r < R; ++r) {
+    const float z = dz[k * R + r];
+    acc.x = fmaf(z, __ldg(W_alpha + (d + 0) * R + r), acc.x);
+    acc.y = fmaf(z, __ldg(W_alpha + (d + 1) * R + r), acc.y);
+    acc.z = fmaf(z, __ldg(W_alpha + (d + 2) * R + r), acc.z);
+    acc.w = fmaf(z, __ldg(W_alpha + (d + 3) * R + r), acc.w);
+  }
+  *p = acc;
 }
 
 int layer_bwd_post(const float* dz, const float* W_alpha, int64_t T, int64_t D, int R, float* dHin, cudaStream_t st) {
   if (T == 0) return IDDGCN_OK;
-  layer_bwd_post_kernel<<<(unsigned)((T * D + 255) / 256), 256, 0, st>>>(dz, W_alpha, T, (int)D, R, dHin);
+  IDD_CHECK(D % 4 == 0, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
+  layer_bwd_post_kernel<<<(unsigned)((T * (D / 4) + 255) / 256), 256, 0, st>>>(dz, W_alpha, T, (int)D, R, dHin);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }
@@ -351,9 +361,17 @@ int segment_scatter(const iddgcn_plan* p, const float* dP, const float* alpha, i
       else if (nvec <= 64) segment_scatter_kernel<2, true, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
       else segment_scatter_kernel<4, true, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
     } else {
-      if (nvec <= 32) segment_scatter_kernel<1, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-      else if (nvec <= 64) segment_scatter_kernel<2, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
-      else segment_scatter_kernel<4, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      // relation planes summed per sweep: no more than there are (R = 2 would otherwise carry two idle planes of
+      // accumulators and compensation terms, and the registers cost a resident block)
+      if (p->R <= 2) {
+        if (nvec <= 32) segment_scatter_kernel<1, true, 2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+        else if (nvec <= 64) segment_scatter_kernel<2, true, 2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+        else segment_scatter_kernel<4, true, 2><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      } else {
+        if (nvec <= 32) segment_scatter_kernel<1, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+        else if (nvec <= 64) segment_scatter_kernel<2, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+        else segment_scatter_kernel<4, true, 4><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
+      }
     }
   } else {
     if (nvec <= 32) segment_scatter_kernel<1, false, 1><<<grid, TW * 32, 0, st>>>(IDD_ARGS);
@@ -605,24 +623,28 @@ __global__ void __launch_bounds__(256)
     adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
                 float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, int64_t step,
                 const int64_t* __restrict__ step_dev) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const int64_t t = step_dev ? *step_dev : step;
-  // double keeps b^t accurate for t in the thousands; one pow per thread is negligible here
+  // double keeps b^t accurate for t in the thousands; the two pow() are paid once per thread, the elements are then
+  // visited with a grid stride (a million-row embedding table would otherwise spend its time in double-precision pow)
   const double c1 = 1.0 - pow((double)b1, (double)t), c2 = 1.0 - pow((double)b2, (double)t);
   const float lr_t = (float)((double)lr * sqrt(c2) / c1);
-  const float g = grad[i];
-  const float mi = b1 * m[i] + (1.0f - b1) * g;
-  const float vi = b2 * v[i] + (1.0f - b2) * g * g;
-  m[i] = mi;
-  v[i] = vi;
-  theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float g = grad[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * g;
+    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
 }
 
 int adam_apply(float* theta, const float* grad, float* m, float* v, int64_t n, float lr, float b1, float b2,
                float eps, int64_t step, const int64_t* step_dev, cudaStream_t st) {
   if (n <= 0) return IDDGCN_OK;
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, eps, step, step_dev);
+  const int64_t blocks = (n + 255) / 256, cap = 16 * (int64_t)sm_count();
+  adam_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, eps, step,
+                                                                     step_dev);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }

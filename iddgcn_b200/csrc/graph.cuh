@@ -42,7 +42,7 @@ struct iddgcn_graph {
   mutable float* host_ws = nullptr;
   mutable size_t host_ws_elems = 0;
   mutable cudaStream_t host_streams[3] = {nullptr, nullptr, nullptr};
-  mutable cudaEvent_t host_events[3] = {nullptr, nullptr, nullptr};
+  mutable cudaEvent_t host_events[16] = {};   // per column panel: X in, dS in, S ready, dX ready (up to 4 panels)
 };
 
 // Triples of one model call, plus the orderings that make every gather-backward a segment sum.

@@ -337,10 +337,10 @@ static void graph_free(iddgcn_graph* g) {
   pool_free(g->heavy_bwd.rows); pool_free(g->heavy_bwd.segptr);
   cudaFree(g->heavy_ws);
   cudaFree(g->host_ws);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 3; ++i)
     if (g->host_streams[i]) cudaStreamDestroy(g->host_streams[i]);
+  for (int i = 0; i < 16; ++i)
     if (g->host_events[i]) cudaEventDestroy(g->host_events[i]);
-  }
   delete g;
 }
 

@@ -827,11 +827,29 @@ int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_
 }
 
 // ---- host-buffer end-to-end path ------------------------------------------------------------
+// The step is PCIe-bound (X + dS in, S + dX out: 3 GB at config 3 against ~3 ms of kernels), so what matters is that both
+// directions of the link stay busy.  Feature columns are independent in an SpMM — S[:, c] needs X[:, c] only and
+// dX[:, c] needs dS[:, c] only — so the buffers travel as P column panels (strided 2-D copies; on the device every panel
+// is a dense [rows, D/P] array the kernels run on directly): S panels start flowing back after the FIRST X panel has
+// landed instead of after all of X, and the last dX panel is 1/P of dX instead of all of it.
+static int host_panels(int64_t D) {
+  // measured at config 3 (D = 128, profiles/README.md): 2 panels of 256-byte row segments 37.3 ms, 1 panel 38.8 ms, 4 panels
+  // of 128-byte segments 49.0 ms — the copy engines lose their rate below 256 bytes per row, so never go narrower
+  int p = D >= 128 ? 2 : 1;
+  if (const char* e = getenv("IDDGCN_HOST_PANELS")) {   // A/B runs
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) p = v;
+  }
+  while (p > 1 && (D % (4 * p)) != 0) p >>= 1;
+  return p;
+}
+
 int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const float* dS_host, int64_t D,
                              float* S_host, float* dX_host) {
   IDD_TRY(check_common(g, D, nullptr, IDDGCN_VALS_ONES));
   IDD_CHECK(X_host && dS_host, IDDGCN_EINVAL, "X_host or dS_host is NULL");
-  const size_t xN = (size_t)g->N * D, sN = (size_t)g->R * g->n_rows * D;
+  const int64_t srows = (int64_t)g->R * g->n_rows;
+  const size_t xN = (size_t)g->N * D, sN = (size_t)srows * D;
   const size_t need = 2 * xN + 2 * sN;
   if (g->host_ws_elems < need) {
     cudaFree(g->host_ws);
@@ -840,42 +858,59 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
     IDD_CUDA(cudaMalloc((void**)&g->host_ws, need * sizeof(float)));
     g->host_ws_elems = need;
   }
-  struct Ws { float* p; } dX_in{g->host_ws}, dS_in{g->host_ws + xN}, dS_out{g->host_ws + xN + sN},
-      dX_out{g->host_ws + xN + 2 * sN};
-  for (int i = 0; i < 3; ++i) {
+  float* X_dev = g->host_ws;                 // [P][N][Dp]
+  float* dS_dev = X_dev + xN;                // [P][srows][Dp]
+  float* S_dev = dS_dev + sN;                // [P][srows][Dp]
+  float* dX_dev = S_dev + sN;                // [P][N][Dp]
+  for (int i = 0; i < 3; ++i)
     if (!g->host_streams[i]) IDD_CUDA(cudaStreamCreateWithFlags(&g->host_streams[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 16; ++i)
     if (!g->host_events[i]) IDD_CUDA(cudaEventCreateWithFlags(&g->host_events[i], cudaEventDisableTiming));
-  }
   cudaStream_t s_in = g->host_streams[0], s_cmp = g->host_streams[1], s_out = g->host_streams[2];
-  cudaEvent_t ev_x = g->host_events[0], ev_ds = g->host_events[1], ev_chunk = g->host_events[2];
-  int rc = IDDGCN_OK;
+  const int P = host_panels(D);
+  const int64_t Dp = D / P;
+  const size_t wbytes = (size_t)Dp * 4, hpitch = (size_t)D * 4;
+  auto ev = [&](int kind, int c) { return g->host_events[kind * 4 + c]; };   // 0: X panel c landed, 1: dS panel c landed
   auto body = [&]() -> int {
-    constexpr int NCHUNK = 8;
-    IDD_CUDA(cudaMemcpyAsync(dX_in.p, X_host, xN * 4, cudaMemcpyHostToDevice, s_in));
-    IDD_CUDA(cudaEventRecord(ev_x, s_in));
-    IDD_CUDA(cudaMemcpyAsync(dS_in.p, dS_host, sN * 4, cudaMemcpyHostToDevice, s_in));
-    IDD_CUDA(cudaEventRecord(ev_ds, s_in));
-    IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev_x, 0));
-    const int64_t srows = (int64_t)g->R * g->n_rows;
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int64_t lo = srows * c / NCHUNK, hi = srows * (c + 1) / NCHUNK;
-      IDD_TRY(spmm_fwd_range(g, dX_in.p, D, nullptr, IDDGCN_VALS_ONES, dS_out.p, lo, hi, s_cmp));
-      if (S_host && hi > lo) {
-        IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
-        IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
-        IDD_CUDA(cudaMemcpyAsync(S_host + (size_t)lo * D, dS_out.p + (size_t)lo * D, (size_t)(hi - lo) * D * 4,
-                                 cudaMemcpyDeviceToHost, s_out));
+    for (int c = 0; c < P; ++c) {
+      IDD_CUDA(cudaMemcpy2DAsync(X_dev + (size_t)c * g->N * Dp, wbytes, X_host + c * Dp, hpitch, wbytes, (size_t)g->N,
+                                 cudaMemcpyHostToDevice, s_in));
+      IDD_CUDA(cudaEventRecord(ev(0, c), s_in));
+    }
+    for (int c = 0; c < P; ++c) {
+      IDD_CUDA(cudaMemcpy2DAsync(dS_dev + (size_t)c * srows * Dp, wbytes, dS_host + c * Dp, hpitch, wbytes,
+                                 (size_t)srows, cudaMemcpyHostToDevice, s_in));
+      IDD_CUDA(cudaEventRecord(ev(1, c), s_in));
+    }
+    // inside a panel the output rows are cut into chunks so that the copy back starts while the kernel still runs
+    const int NCHUNK = 8 / P;
+    cudaEvent_t ev_chunk = g->host_events[15];
+    for (int c = 0; c < P; ++c) {
+      IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev(0, c), 0));
+      float* Sp = S_dev + (size_t)c * srows * Dp;
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int64_t lo = srows * q / NCHUNK, hi = srows * (q + 1) / NCHUNK;
+        IDD_TRY(spmm_fwd_range(g, X_dev + (size_t)c * g->N * Dp, Dp, nullptr, IDDGCN_VALS_ONES, Sp, lo, hi, s_cmp));
+        if (S_host && hi > lo) {
+          IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
+          IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
+          IDD_CUDA(cudaMemcpy2DAsync(S_host + (size_t)lo * D + c * Dp, hpitch, Sp + (size_t)lo * Dp, wbytes, wbytes,
+                                     (size_t)(hi - lo), cudaMemcpyDeviceToHost, s_out));
+        }
       }
     }
-    IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev_ds, 0));
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int64_t lo = g->N * c / NCHUNK, hi = g->N * (c + 1) / NCHUNK;
-      IDD_TRY(spmm_bwd_x_range(g, dS_in.p, D, nullptr, IDDGCN_VALS_ONES, dX_out.p, 0, lo, hi, s_cmp));
-      if (dX_host && hi > lo) {
-        IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
-        IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
-        IDD_CUDA(cudaMemcpyAsync(dX_host + (size_t)lo * D, dX_out.p + (size_t)lo * D, (size_t)(hi - lo) * D * 4,
-                                 cudaMemcpyDeviceToHost, s_out));
+    for (int c = 0; c < P; ++c) {
+      IDD_CUDA(cudaStreamWaitEvent(s_cmp, ev(1, c), 0));
+      float* dXp = dX_dev + (size_t)c * g->N * Dp;
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int64_t lo = g->N * q / NCHUNK, hi = g->N * (q + 1) / NCHUNK;
+        IDD_TRY(spmm_bwd_x_range(g, dS_dev + (size_t)c * srows * Dp, Dp, nullptr, IDDGCN_VALS_ONES, dXp, 0, lo, hi, s_cmp));
+        if (dX_host && hi > lo) {
+          IDD_CUDA(cudaEventRecord(ev_chunk, s_cmp));
+          IDD_CUDA(cudaStreamWaitEvent(s_out, ev_chunk, 0));
+          IDD_CUDA(cudaMemcpy2DAsync(dX_host + (size_t)lo * D + c * Dp, hpitch, dXp + (size_t)lo * Dp, wbytes, wbytes,
+                                     (size_t)(hi - lo), cudaMemcpyDeviceToHost, s_out));
+        }
       }
     }
     IDD_CUDA(cudaStreamSynchronize(s_cmp));
@@ -883,7 +918,7 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
     IDD_CUDA(cudaStreamSynchronize(s_in));
     return IDDGCN_OK;
   };
-  rc = body();
+  const int rc = body();
   if (rc != IDDGCN_OK) cudaDeviceSynchronize();
   return rc;
 }

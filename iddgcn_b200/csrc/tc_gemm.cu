@@ -27,7 +27,7 @@ namespace {
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_KB = 32;                              // floats per k-block = one 128-byte swizzle row
 constexpr int TC_THREADS = 384;
-constexpr int TC_PREFETCH_TILES = 2;                   // L2 prefetch distance, in tiles of this CTA
+constexpr int TC_PREFETCH_TILES = 1;                   // L2 prefetch distance in tiles of this CTA (swept 0-4: 1 is best)
 constexpr int TC_A_SLAB = TC_BLOCK_M * TC_KB * 4;      // 16 KB: one A k-block (hi or lo)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       uint32_t it = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t ahead = tile + (int64_t)TC_PREFETCH_TILES * gridDim.x;   // this CTA's tile after next: into L2 now
+        const int64_t ahead = tile + (int64_t)TC_PREFETCH_TILES * gridDim.x;   // this CTA's next tile: into L2 now
         if (ahead < tiles)
           for (int kb = 0; kb < KBLOCKS; ++kb) tma_prefetch_l2_2d(&map_a, kb * TC_KB, (int)(ahead * TC_BLOCK_M));
         for (int kb = 0; kb < KBLOCKS; ++kb, ++it) {
@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               for (int e = 0; e < 8; ++e) v[j + e] = __float_as_uint(__uint_as_float(v[j + e]) + old[e]);
             }
           }
+#pragma unroll
 #pragma unroll
           for (int j = 0; j < 32; j += 8) st_global_v8(crow + c0 + j, v + j);
         }

@@ -42,7 +42,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spins on the phase with the given parity.  A wait that lasts seconds can only be a protocol bug: trap instead of
+// Spins on the phase with the given parity.  A single wait that lasts ~10 s of SM clock can only be a protocol bug
+// (legitimate waits are microseconds, and a time-sliced GPU stretches them by slices, not by seconds): trap instead of
 // hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
@@ -56,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -500,7 +500,8 @@ int iddgcn_dense_transform(const float* A, const float* W, int64_t M, int64_t D,
   if (path == 1) return gemm_f32_simt(false, trans_w != 0, M, D, D, A, D, 0, W, D, 0, C, D, 0, 1, accumulate != 0, st);
   if (path == 2) {
     IDD_CHECK(tc_gemm_eligible(false, M, D, D, A, D, W, D, C, D, 1), IDDGCN_EINVAL,
-              "the tensor-core path needs D in {64, 128} and 16-byte aligned buffers (D=%lld)", (long long)D);
+              "the tensor-core path needs D in {64, 128}, A and W 16-byte aligned and C 32-byte aligned (D=%lld)",
+              (long long)D);
     return gemm_tf32x3(trans_w != 0, M, D, D, A, D, 0, W, 0, C, D, 0, 1, accumulate != 0, st);
   }
   return gemm_f32(false, trans_w != 0, M, D, D, A, D, 0, W, D, 0, C, D, 0, 1, accumulate != 0, st);

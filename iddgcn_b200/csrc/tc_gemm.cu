@@ -731,9 +731,10 @@ bool tc_gemm_enabled() {
 bool tc_gemm_eligible(bool transA, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                       int64_t ldb, const float* C, int64_t ldc, int64_t min_rows) {
   if (transA || N != K || (N != 64 && N != 128) || M < min_rows || M >= ((int64_t)1 << 31) - TC_BLOCK_M) return false;
-  if (ldb != N || (lda % 4) != 0 || (ldc % 4) != 0 || lda < K || ldc < N) return false;
-  const uintptr_t bits = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C);
-  return (bits & 15u) == 0;
+  // TMA wants 16-byte aligned rows of A; the epilogue moves C with 256-bit accesses, so C rows must be 32-byte aligned
+  if (ldb != N || (lda % 4) != 0 || (ldc % 8) != 0 || lda < K || ldc < N) return false;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B);
+  return (bits & 15u) == 0 && (reinterpret_cast<uintptr_t>(C) & 31u) == 0;
 }
 
 // C[b] (+)= A[b] · op(B[b]) with op(B) = B (B is [K,N] row-major) when !transB, Bᵀ (B is [N,K]) when transB.

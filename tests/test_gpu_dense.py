@@ -96,6 +96,25 @@ def test_tensor_core_path_rejects_other_widths():
     assert np.isfinite(_transform(A, W, 0, None, path=0)).all()                  # automatic falls back to SIMT
 
 
+def test_misaligned_output_falls_back_or_is_refused():
+    """The tensor-core epilogue stores 256 bits at a time: a C that is only 16-byte aligned is refused on the forced
+    path and silently served by the SIMT kernels on the automatic one."""
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    M, D = 40000, 64
+    A, W, _ = _case(M, D, seed=2)
+    a, w = torch.as_tensor(A, device=dev), torch.as_tensor(W, device=dev)
+    buf = torch.zeros(M * D + 8, device=dev)
+    c = buf[4:4 + M * D]                                                     # 16-byte aligned, not 32
+    assert c.data_ptr() % 32 == 16
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with pytest.raises(_lib.IddgcnError):
+        _lib.check(lib.iddgcn_dense_transform(_lib.ptr(a), _lib.ptr(w), M, D, 0, c.data_ptr(), 0, 2, st))
+    _lib.check(lib.iddgcn_dense_transform(_lib.ptr(a), _lib.ptr(w), M, D, 0, c.data_ptr(), 0, 0, st))
+    torch.cuda.synchronize()
+    assert _scaled_err(c.view(M, D).cpu().numpy(), A, W, 0, None) < SIMT_TOL
+
+
 def test_many_tiles_per_cta_and_determinism():
     """More tiles than SMs (the persistent loop wraps the stage ring and both accumulators many times), run twice."""
     A, W, C0 = _case(148 * 128 * 5 + 77, 64, seed=9)

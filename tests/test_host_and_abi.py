@@ -180,3 +180,19 @@ def test_product_ground_truth_and_metrics_match_oracle(golden_dir, tmp_path):
     E.save_ground_truth(tmp_path / "gt.npz", kept, gts)
     kept2, gts2 = E.load_ground_truth(tmp_path / "gt.npz")
     assert np.array_equal(kept2, kept) and gts2 == gts
+
+
+def test_ground_truth_loader_reads_the_reference_container(tmp_path):
+    """gt_process.py:39 stores the ground truth as a pickled object array under 'result'; the loader opens it only when
+    the caller opts in, and refuses (NumPy's ValueError) otherwise."""
+    from iddgcn_b200 import explain_eval as E
+    gt = [[[1.0, 0.0, 700.0], [700.0, 2.0, 701.0]], [[5.0, 1.0, 690.0]]]
+    path = tmp_path / "gt_filtered_fold9.npz"
+    np.savez(path, result=np.array(gt, dtype=object))
+    with pytest.raises(ValueError):
+        E.load_ground_truth(path)
+    triples, back = E.load_ground_truth(path, allow_pickle=True)
+    assert triples is None and back == gt
+    preds = [np.array([[1, 0, 700], [9, 9, 9]]), np.array([[690, 1, 5]])]
+    (p0, r0, _), (p1, r1, _) = E.explanation_metrics(preds, back)
+    assert (p0, r0) == (0.2, 0.1) and (p1, r1) == (0.2, 0.1)

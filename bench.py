@@ -1,20 +1,22 @@
 #!/usr/bin/env python3
-"""bench.py — relational SpMM fwd+bwd throughput (edges/s) on B200, with roofline and CPU baseline.
+"""bench.py — relational SpMM fwd+bwd throughput (edges/s) on B200, with roofline, CPU baseline and in-run parity.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c4|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c3|small|c3zipf]
+                    [--grid RxC] [--exchange p2p|nccl]
 
 A "step" is one pass of the hot path over one synthetic graph: S_r = A_r·X for every relation
 (iddgcn_spmm_fwd) followed by dX = Σ_r A_rᵀ·dS_r (iddgcn_spmm_bwd_x).  edges = Σ_r nnz_r (deduplicated).
-Workloads (BASELINE.json configs[2]/[3]):
-  c3    N=1M nodes, 2 relations x 10M raw edges, D=128, one B200.  With --gpus P the graph is P x c3
-        (P·1M nodes, P·20M edges), destination rows partitioned into P blocks of 1M rows (weak scaling):
-        per step every rank all-gathers the feature blocks (NCCL), runs its row block fwd + bwd, and
-        reduce-scatters the partial dX.
-  c4    N=20M nodes, 2 x 100M raw edges, D=128, same partitioning, total work fixed (strong scaling).
-  small N=100k, 2 x 1M edges (smoke-sized).
-Timing: CUDA events on the launching stream, W warm-up steps then K timed steps bracketed by barrier +
-synchronize; max over ranks.  Inputs (X 0.5 GB, dS 1 GB, S 1 GB at c3) are far larger than the 126 MB
-L2, so no explicit flush is needed between iterations (stated in config.l2).
+Workloads (BASELINE.json configs[2]/[3]; graph recipe: per relation r, np.random.default_rng(r)
+.integers(0, N, per_rel) for heads then tails — the same function feeds both arms):
+  c4    N=20M nodes, 2 x 100M raw edges, D=128 — BASELINE configs[3], the default at every --gpus N (strong
+        scaling: the graph is fixed, the ranks form a P_r x P_c grid of destination-row blocks x feature-column
+        groups, see iddgcn_b200/dist.py; it fits one B200, so N=1 runs the same graph).
+  c3    N=1M nodes, 2 x 10M raw edges, D=128 — BASELINE configs[2]; with --gpus P the graph is P x c3 (weak scaling).
+  small N=100k, 2 x 1M edges (smoke-sized).   c3zipf: c3 with Zipf(1.2) destination degrees.
+Timing: CUDA events on the launching stream, W warm-up steps then K timed steps bracketed by barrier + synchronize;
+max over ranks.  Inputs are far larger than the 126 MB L2, so no explicit flush is needed between iterations.
+After the timed region every rank checks sampled rows of S and dX against oracle/spmm_ref.c evaluated on the RAW edge
+list (independent of the device graph build and of the exchange) and the line carries "parity_check".
 """
 from __future__ import annotations
 
@@ -32,11 +34,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c3": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak"),
     "c4": dict(N=20_000_000, R=2, per_rel=100_000_000, D=128, scaling="strong"),
+    "c3": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak"),
     "small": dict(N=100_000, R=2, per_rel=1_000_000, D=128, scaling="weak"),
     # skewed variant of c3: destination degrees ~ Zipf(s=1.2), same raw edge count
     "c3zipf": dict(N=1_000_000, R=2, per_rel=10_000_000, D=128, scaling="weak", zipf=1.2),
+}
+LABELS = {
+    "c4": "synthetic 20M-node / 200M-edge 2-relation graph, D=128 (BASELINE configs[3])",
+    "c3": "synthetic 1M-node / 20M-edge 2-relation directed graph, D=128 (BASELINE configs[2]); xP at --gpus P (weak)",
+    "small": "synthetic 100k-node / 2M-edge 2-relation graph, D=128 (smoke size)",
+    "c3zipf": "config-3 shape with Zipf(1.2) destination degrees (skewed variant, SURVEY 8d)",
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -109,37 +117,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed, zipf=None):
-    """Uniform random directed edges (SURVEY §8d recipe, generated on device): per relation
-    per_rel_total (head, tail) pairs; a rank keeps only heads inside its row block."""
-    dev = torch.device("cuda", torch.cuda.current_device())
-    out = []
-    chunk = 25_000_000
-    for r in range(R):
-        gen = torch.Generator(device=dev).manual_seed(seed * 1000 + r)
-        left = per_rel_total
-        while left > 0:
-            n = min(chunk, left)
-            if zipf:   # inverse-CDF sampling of rank k with p(k) ~ k^-s, ranks scattered by a fixed permutation
-                if r == 0 and left == per_rel_total:
-                    w = torch.arange(1, N_total + 1, device=dev, dtype=torch.float64).pow(-float(zipf))
-                    cdf = torch.cumsum(w, 0) / w.sum()
-                    scatter = torch.randperm(N_total, device=dev, generator=gen)
-                u = torch.rand(n, device=dev, generator=gen, dtype=torch.float64)
-                h = scatter[torch.searchsorted(cdf, u).clamp_(max=N_total - 1)]
-            else:
-                h = torch.randint(0, N_total, (n,), device=dev, generator=gen)
-            t = torch.randint(0, N_total, (n,), device=dev, generator=gen)
-            if row_lo != 0 or row_hi != N_total:
-                keep = (h >= row_lo) & (h < row_hi)
-                h, t = h[keep], t[keep]
-            out.append(torch.stack([h, torch.full_like(h, r), t], 1))
-            left -= n
-    return torch.cat(out, 0)
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs shared by both arms
+# ------------------------------------------------------------------------------------------------
+def raw_edges(N, per_rel, r, zipf=None):
+    """Relation r of the SURVEY §8d recipe: per_rel (head, tail) pairs, uniform (or Zipf-skewed heads), int64."""
+    g = np.random.default_rng(r)
+    if zipf:
+        w = np.arange(1, N + 1, dtype=np.float64) ** -float(zipf)
+        cdf = np.cumsum(w) / w.sum()
+        scatter = np.random.default_rng(12345).permutation(N)
+        h = scatter[np.minimum(np.searchsorted(cdf, g.random(per_rel)), N - 1)]
+    else:
+        h = g.integers(0, N, per_rel)
+    t = g.integers(0, N, per_rel)
+    return h, t
+
+
+# Counter-based feature generator: element (row, col) of X or dS is a hash of its GLOBAL position, so any rank — and
+# the host-side parity check — can produce any row without communication.  splitmix64 finaliser; torch (signed
+# int64 with masked shifts) and NumPy (uint64) versions give identical bits.
+_GOLD, _M1, _M2 = 0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+_STREAM = {"X": 0x1234 << 40, "dS": 0x4321 << 40}
+
+
+def _s64(x):
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _finish_np(u24, kind):
+    u = u24.astype(np.float32) * np.float32(2.0 ** -24)
+    return u if kind == "X" else (u - np.float32(0.5)) * np.float32(3.4641016)
+
+
+def gen_rows_np(kind, row_ids, col_lo, Dc, D_total):
+    """NumPy: rows `row_ids` (global flattened ids), columns [col_lo, col_lo+Dc) -> float32 [len, Dc]."""
+    idx = (np.asarray(row_ids, np.uint64)[:, None] * np.uint64(D_total)
+           + (np.uint64(col_lo) + np.arange(Dc, dtype=np.uint64))[None, :] + np.uint64(_STREAM[kind]))
+    z = idx + np.uint64(_GOLD)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(_M1)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(_M2)
+    z = z ^ (z >> np.uint64(31))
+    return _finish_np(z >> np.uint64(40), kind)
+
+
+def gen_rows_torch(torch, kind, row_ids, col_lo, Dc, D_total):
+    """torch (any device): same values as gen_rows_np."""
+    cols = torch.arange(col_lo, col_lo + Dc, dtype=torch.int64, device=row_ids.device)
+    z = row_ids.to(torch.int64)[:, None] * D_total + cols[None, :] + (_STREAM[kind] + _s64(_GOLD))
+    z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _s64(_M1)
+    z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _s64(_M2)
+    z = z ^ ((z >> 31) & ((1 << 33) - 1))
+    u = ((z >> 40) & 0xFFFFFF).to(torch.float32) * (2.0 ** -24)
+    return u if kind == "X" else (u - 0.5) * 3.4641016
+
+
+def fill_rows(torch, out, kind, first_row, col_lo, D_total, chunk_elems=1 << 25):
+    """out [n, Dc] (device) <- generator rows first_row .. first_row+n."""
+    n, Dc = out.shape
+    step = max(1, chunk_elems // Dc)
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        ids = torch.arange(first_row + a, first_row + b, dtype=torch.int64, device=out.device)
+        out[a:b].copy_(gen_rows_torch(torch, kind, ids, col_lo, Dc, D_total))
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle; the one place bench.py executes oracle/)
+# CPU baseline (oracle; the one place bench.py executes oracle/ besides the parity check)
 # ------------------------------------------------------------------------------------------------
 def host_threads():
     """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the
@@ -148,6 +192,29 @@ def host_threads():
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+def host_mem_short(need_bytes):
+    """True when pinning need_bytes of host memory would leave less than 25 % + 8 GB of headroom."""
+    try:
+        with open("/proc/meminfo") as f:
+            avail = next(int(l.split()[1]) * 1024 for l in f if l.startswith("MemAvailable"))
+        limit = avail
+        for p in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+            try:
+                v = open(p).read().strip()
+                if v.isdigit():
+                    limit = min(limit, int(v))
+            except OSError:
+                pass
+        host_mem_short.last = f"need {need_bytes / 1e9:.1f} GB, available {limit / 1e9:.1f} GB"
+        return limit < 1.25 * need_bytes + (8 << 30)
+    except Exception:
+        host_mem_short.last = "unknown"
+        return False
+
+
+host_mem_short.last = ""
 
 
 def cpu_baseline_run(struct, N, n_rows, R, D, X, dS, passes, threads=0):
@@ -166,25 +233,22 @@ def cpu_baseline_run(struct, N, n_rows, R, D, X, dS, passes, threads=0):
     return times, threads
 
 
-def cpu_sample_inputs(wl, seed=0):
-    """Host-side (NumPy) generation of the CPU arm's inputs with the SURVEY §8d recipe.  c3/small run
-    the FULL workload; c4 (200M edges) is bounded to the same generator at 1/8 scale."""
-    rng = np.random.default_rng(seed)
+def cpu_sample_inputs(wl):
+    """Host-side inputs of the CPU arm: the SAME recipe (raw_edges + counter-hash features).  c3/small run the FULL
+    workload (the very graph the GPU arm builds); c4 (200M edges) is bounded to the recipe at 1/8 scale."""
     frac = 8 if wl["per_rel"] > 20_000_000 else 1
     N, R, D = wl["N"] // frac, wl["R"], wl["D"]
-    n_rows = N
     per_rel = wl["per_rel"] // frac
     rows_all, cols_all, perm_all, crow_all = [], [], [], []
-    rowptr = np.zeros(R * n_rows + 1, np.int64)
+    rowptr = np.zeros(R * N + 1, np.int64)
     cptr = np.zeros(R * N + 1, np.int64)
     off = 0
     for r in range(R):
-        h = rng.integers(0, n_rows, per_rel)
-        t = rng.integers(0, N, per_rel)
+        h, t = raw_edges(N, per_rel, r, wl.get("zipf"))
         key = np.unique(h * N + t)                      # dedup + (head, tail) order = CSR order
         rows, cols = key // N, key % N
-        rowptr[r * n_rows + 1:(r + 1) * n_rows + 1] = off + np.cumsum(np.bincount(rows, minlength=n_rows))
-        order = np.argsort(cols * n_rows + rows, kind="stable")      # (tail, head) order = CSC order
+        rowptr[r * N + 1:(r + 1) * N + 1] = off + np.cumsum(np.bincount(rows, minlength=N))
+        order = np.argsort(cols * N + rows, kind="stable")      # (tail, head) order = CSC order
         cptr[r * N + 1:(r + 1) * N + 1] = off + np.cumsum(np.bincount(cols, minlength=N))
         rows_all.append(rows); cols_all.append(cols); perm_all.append(order + off); crow_all.append(rows[order])
         off += len(key)
@@ -192,11 +256,16 @@ def cpu_sample_inputs(wl, seed=0):
     struct = {"csr_rowptr": rowptr.astype(np.int32), "csr_col": np.concatenate(cols_all).astype(np.int32),
               "csc_rowptr": cptr.astype(np.int32), "csc_row": np.concatenate(crow_all).astype(np.int32),
               "csc_perm": np.concatenate(perm_all).astype(np.int32)}
-    X = rng.random((N, D), dtype=np.float32)
-    dS = rng.standard_normal((R * n_rows, D), dtype=np.float32)
-    scale = "full workload" if frac == 1 else f"same generator at 1/{frac} scale"
+    X = np.empty((N, D), np.float32)
+    dS = np.empty((R * N, D), np.float32)
+    step = 1 << 18
+    for a in range(0, N, step):
+        X[a:a + step] = gen_rows_np("X", np.arange(a, min(N, a + step)), 0, D, D)
+    for a in range(0, R * N, step):
+        dS[a:a + step] = gen_rows_np("dS", np.arange(a, min(R * N, a + step)), 0, D, D)
+    scale = "full workload, same graph as the GPU arm" if frac == 1 else f"same recipe at 1/{frac} scale"
     sample = f"{wl['name']} ({scale}): {N} nodes, {nnz} edges, R={R}, D={D}, one fwd+bwd pass per step"
-    return struct, N, n_rows, nnz, X, dS, sample
+    return struct, N, nnz, X, dS, sample
 
 
 def run_reference(args, wl):
@@ -204,10 +273,10 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    struct, N, n_rows, nnz, X, dS, sample = cpu_sample_inputs(wl)
+    struct, N, nnz, X, dS, sample = cpu_sample_inputs(wl)
     R, D = wl["R"], wl["D"]
-    cpu_baseline_run(struct, N, n_rows, R, D, X, dS, max(args.warmup, 1))
-    times, cores = cpu_baseline_run(struct, N, n_rows, R, D, X, dS, args.steps)
+    cpu_baseline_run(struct, N, N, R, D, X, dS, max(args.warmup, 1))
+    times, cores = cpu_baseline_run(struct, N, N, R, D, X, dS, args.steps)
     total = sum(times)
     value = nnz * args.steps / total
     line = {
@@ -223,12 +292,81 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------
+# in-run parity check against the C oracle
+# ------------------------------------------------------------------------------------------------
+def parity_check(torch, eng, raw, N_total, R, D, n_sample, seed):
+    """Sampled rows of this rank's S and dX against oracle/spmm_ref.c on the RAW edge list.
+
+    Nothing the device computed enters the reference: the edges come from the host-side recipe (so the device graph
+    build, dedup included, is under test), the input rows from the counter-hash generator (so the all-gather and the
+    fused reduce-scatter are under test).  Returns per-rank maxima; bench reduces them over ranks."""
+    from oracle import cref
+    dev = eng.dev
+    Dc, col_lo, lo, n_rows = eng.Dc, eng.pc * eng.Dc, eng.lo, eng.n_rows
+    rng = np.random.default_rng(seed)
+    m = min(n_sample, n_rows)
+    if m <= 0:
+        return {"rows": 0, "max_abs_err": 0.0, "max_rel_err": 0.0, "edges": 0}
+    picked = np.sort(rng.choice(n_rows, m, replace=False)) if m < n_rows else np.arange(n_rows)
+    gid = picked + lo                                   # global ids: destination rows for S, source nodes for dX
+    lut = np.full(N_total, -1, np.int32)
+    lut[gid] = np.arange(m, dtype=np.int32)
+    threads = host_threads()
+
+    def gen(kind, ids):                                 # generator rows on the device, then to the host
+        out = np.empty((len(ids), Dc), np.float32)
+        step = 1 << 20
+        for a in range(0, len(ids), step):
+            t = torch.from_numpy(np.ascontiguousarray(ids[a:a + step])).to(dev)
+            out[a:a + step] = gen_rows_torch(torch, kind, t, col_lo, Dc, D).cpu().numpy()
+        return out
+
+    # --- forward: S[r, row] = Σ_{unique (row -> t) in relation r} X[t]
+    ptr = np.zeros(R * m + 1, np.int64)
+    cols = []
+    for r, (h, t) in enumerate(raw):
+        li = lut[h]
+        sel = li >= 0
+        key = np.unique(li[sel].astype(np.int64) * N_total + t[sel])
+        ptr[r * m + 1:(r + 1) * m + 1] = np.bincount(key // N_total, minlength=m)
+        cols.append(key % N_total)
+    ptr = np.cumsum(ptr)
+    cols = np.concatenate(cols)
+    ucols, inv = np.unique(cols, return_inverse=True)
+    S_ref = cref.spmm_csr(ptr.astype(np.int32), inv.astype(np.int32), None, gen("X", ucols), threads=threads)
+    sel_dev = torch.from_numpy(picked).to(dev)
+    S_dev = eng.S[:, sel_dev].reshape(R * m, Dc).cpu().numpy()
+    e_fwd = float(np.abs(S_dev - S_ref).max())
+    s_fwd = float(np.abs(S_ref).max())
+    n_edges = int(len(cols))
+    # --- backward: dX[k] = Σ_r Σ_{unique (h -> k) in relation r} dS[r, h]   (relation-major, ascending head)
+    keys = []
+    for r, (h, t) in enumerate(raw):
+        li = lut[t]
+        sel = li >= 0
+        keys.append(np.unique(li[sel].astype(np.int64) * (R * N_total) + (r * N_total + h[sel])))
+    key = np.sort(np.concatenate(keys))
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(key // (R * N_total), minlength=m))])
+    src = key % (R * N_total)
+    usrc, inv = np.unique(src, return_inverse=True)
+    dX_ref = cref.spmm_csr(ptr.astype(np.int32), inv.astype(np.int32), None, gen("dS", usrc), threads=threads)
+    dX_dev = eng.dX[sel_dev].cpu().numpy()
+    e_bwd = float(np.abs(dX_dev - dX_ref).max())
+    s_bwd = float(np.abs(dX_ref).max())
+    n_edges += int(len(src))
+    return {"rows": int(m), "edges": n_edges, "max_abs_err": max(e_fwd, e_bwd),
+            "max_rel_err": max(e_fwd / (s_fwd + 1e-30), e_bwd / (s_bwd + 1e-30)),
+            "fwd_rel_err": e_fwd / (s_fwd + 1e-30), "bwd_rel_err": e_bwd / (s_bwd + 1e-30)}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
     from iddgcn_b200 import _lib, ops
+    from iddgcn_b200.dist import GridSpMM, parse_grid, grid_coords, row_block
     from iddgcn_b200.graph import Graph
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,22 +375,35 @@ def run_ours(args, wl):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL on a high-priority stream: its few CTAs must be scheduled while the gather kernel's 250k blocks are
-        # still queued, otherwise the exchange only starts at the tail of each SpMM launch and nothing overlaps.
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-        rs_group = dist.new_group(backend="nccl", pg_options=opts)   # second communicator: reduce-scatter stream
+        dist.init_process_group("nccl", device_id=dev)
     R, D = wl["R"], wl["D"]
     if wl["scaling"] == "weak":
         N_total, per_rel_total = wl["N"] * world, wl["per_rel"] * world
     else:
         N_total, per_rel_total = wl["N"], wl["per_rel"]
-    block = (N_total + world - 1) // world
-    row_lo, row_hi = rank * block, min((rank + 1) * block, N_total)
+    grid = parse_grid(args.grid, world, D)
+    pr, pc = grid_coords(rank, grid)
+    row_lo, row_hi, block = row_block(pr, grid[0], N_total)
     n_rows = row_hi - row_lo
+    Dc = D // grid[1]
 
-    tri = make_triples(torch, N_total, R, per_rel_total, row_lo, row_hi, seed=7, zipf=wl.get("zipf"))
+    # graph: the raw edge list of the recipe (host), this rank's row block built on the device
+    t0 = time.perf_counter()
+    raw = [raw_edges(N_total, per_rel_total, r, wl.get("zipf")) for r in range(R)]
+    gen_s = time.perf_counter() - t0
+    parts = []
+    for r, (h, t) in enumerate(raw):
+        if grid[0] > 1:
+            keep = (h >= row_lo) & (h < row_hi)
+            h, t = h[keep], t[keep]
+        tri = torch.empty((len(h), 3), dtype=torch.int64, device=dev)
+        tri[:, 0].copy_(torch.from_numpy(h))
+        tri[:, 1].fill_(r)
+        tri[:, 2].copy_(torch.from_numpy(t))
+        parts.append(tri)
+    tri = torch.cat(parts, 0) if len(parts) > 1 else parts[0]
+    del parts
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     g = Graph(tri, N_total, R, row_block=(row_lo, row_hi))
     torch.cuda.synchronize()
@@ -260,25 +411,23 @@ def run_ours(args, wl):
     del tri
     torch.cuda.empty_cache()
     nnz_local = g.nnz
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    X_local = torch.rand((n_rows, D), device=dev, generator=gen)      # this rank's block of the features
-    dS = torch.randn((R, n_rows, D), device=dev, generator=gen)
-    S = torch.empty((R, n_rows, D), device=dev)
+
+    eng = GridSpMM(g, D, world, rank, grid, exchange=args.exchange)
+    fill_rows(torch, eng.x_local_view(), "X", row_lo, pc * Dc, D)
+    for r in range(R):
+        fill_rows(torch, eng.dS[r], "dS", r * N_total + row_lo, pc * Dc, D)
+    # the two generators must agree bit for bit (the parity check relies on it)
+    probe = np.array([0, 1, N_total - 1, 12345 % N_total], np.int64)
+    for kind in ("X", "dS"):
+        a = gen_rows_torch(torch, kind, torch.from_numpy(probe).to(dev), pc * Dc, Dc, D).cpu().numpy()
+        assert np.array_equal(a, gen_rows_np(kind, probe, pc * Dc, Dc, D)), "device / host generators disagree"
     if world > 1:
-        from iddgcn_b200.dist import PartitionedSpMM
-        engine = PartitionedSpMM(g, D, world, rank, block, panels=args.panels, rs_group=rs_group,
-                                 exchange=args.exchange, mc_ctas=args.mc_ctas)
-        step = lambda: engine.step(X_local, dS, S)
-        nnz_t = torch.tensor([nnz_local], device=dev, dtype=torch.int64)
+        nnz_t = torch.tensor([nnz_local if pc == 0 else 0], device=dev, dtype=torch.int64)
         dist.all_reduce(nnz_t)
         nnz_global = int(nnz_t.item())
     else:
-        dX = torch.empty((N_total, D), device=dev)
-
-        def step():
-            ops.spmm_fwd(g, X_local, out=S)
-            ops.spmm_bwd_x(g, dS, out=dX)
         nnz_global = nnz_local
+    step = eng.step
 
     def barrier():
         if world > 1:
@@ -291,7 +440,7 @@ def run_ours(args, wl):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # A timed region of K x 3 ms is shorter than nvidia-smi's sampling period, so the clock sampler first watches
+    # A timed region of K steps can be shorter than nvidia-smi's sampling period, so the clock sampler first watches
     # ~0.5 s of the same step (untimed, extra warm-up) and keeps running through the timed region that follows.
     t_load = time.perf_counter()
     step()
@@ -312,6 +461,7 @@ def run_ours(args, wl):
     barrier()
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    eng.check_timeouts()
     total_ms = ev0.elapsed_time(ev1)
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -320,71 +470,101 @@ def run_ours(args, wl):
     ms_per_step = total_ms / args.steps
     value = nnz_global / (ms_per_step * 1e-3)
 
+    # in-run parity: every rank checks its share of --check-rows sampled rows (all rows when the block is smaller)
+    parity = None
+    if args.check_rows > 0:
+        t0 = time.perf_counter()
+        pch = parity_check(torch, eng, raw, N_total, R, D, max(1, args.check_rows // world), seed=1000 + rank)
+        if world > 1:
+            v = torch.tensor([pch["max_abs_err"], pch["max_rel_err"], pch["fwd_rel_err"], pch["bwd_rel_err"]],
+                             dtype=torch.float64, device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            c = torch.tensor([pch["rows"], pch["edges"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(c)
+            pch.update(max_abs_err=float(v[0]), max_rel_err=float(v[1]), fwd_rel_err=float(v[2]),
+                       bwd_rel_err=float(v[3]), rows=int(c[0]), edges=int(c[1]))
+        pch.update(tolerance=1e-5, ok=bool(pch["max_rel_err"] <= 1e-5), ranks=world,
+                   reference="oracle/spmm_ref.c on the raw edge list (sampled S rows and dX rows per rank, every rank)",
+                   norm="max |gpu - ref| / max |ref|", seconds=time.perf_counter() - t0)
+        parity = pch
+    del raw
+
     # per-kernel timing (events on the launching stream) for the roofline of the dominant kernel
-    kt = {"fwd": [], "bwd": []}
+    kt = eng.kernel_times(iters=max(args.steps, 5))
     comm = None
-    if world == 1:
-        for _ in range(max(args.steps, 5)):
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            a.record(); ops.spmm_fwd(g, X_local, out=S); b.record(); ops.spmm_bwd_x(g, dS, out=dX); c.record()
-            torch.cuda.synchronize()
-            kt["fwd"].append(a.elapsed_time(b)); kt["bwd"].append(b.elapsed_time(c))
-    else:
-        kt = engine.kernel_times(X_local, dS, S, iters=max(args.steps, 5))
-        ct = engine.comm_times(iters=5)
-        comm = {k: float(np.mean(v)) for k, v in ct.items()}
-        comm["bytes_received_per_rank"] = int((world - 1) * block * D * 4)
-        comm["all_gather_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["all_gather"] / 1e6
-        comm["reduce_scatter_GBps_per_rank"] = comm["bytes_received_per_rank"] / comm["reduce_scatter"] / 1e6
-        # NVLink bound for the exchange of one step (B200_PROFILING.md: measured 770 GB/s per direction per GPU):
-        # every rank receives (P-1) blocks in the all-gather and sends (P-1) blocks in the reduce-scatter, and ring
-        # collectives load both directions, so the two legs cannot overlap each other
-        comm["nvlink_GBps_per_direction"] = 770.0
-        comm["nvlink_bound_ms"] = 2 * comm["bytes_received_per_rank"] / 770.0 / 1e6
-        comm["step_over_nvlink_bound"] = ms_per_step / comm["nvlink_bound_ms"]
-        comm["panels"] = engine.panels
-        comm["exchange"] = args.exchange
+    if world > 1:
+        comm = {"grid": f"{grid[0]}x{grid[1]}", "exchange": eng.exchange,
+                "bytes_exchanged_per_rank_each_way": int((grid[0] - 1) * block * Dc * 4)}
+        et = eng.exchange_times(iters=5) if eng.exchange == "p2p" else None
+        if et:
+            comm["all_gather_push_ms_alone"] = float(np.median(et["all_gather_push"]))
+            comm["partial_push_dma_ms_alone"] = float(np.median(et["partial_push"]))
+            b = comm["bytes_exchanged_per_rank_each_way"]
+            comm["all_gather_push_GBps"] = b / comm["all_gather_push_ms_alone"] / 1e6
+            # NVLink bound (B200_PROFILING.md: ~770 GB/s per direction per GPU): each rank sends its X block and its
+            # partials to P_r-1 peers -> 2 x bytes out, and receives as much
+            comm["nvlink_bound_ms"] = 2 * b / 770.0 / 1e6
+        fwd_k, bwd_k = float(np.median(kt["fwd"])), float(np.median(kt["bwd"]))
+        comm["kernels_ms"] = fwd_k + bwd_k
+        comm["step_over_kernels"] = ms_per_step / (fwd_k + bwd_k)
+        comm["limiter"] = ("kernels (exchange hidden)" if ms_per_step < 1.15 * (fwd_k + bwd_k) else
+                           "exchange / waits not fully hidden behind the kernels")
     sddmm = None
-    if world == 1:
+    if world == 1 and not args.no_sddmm:
         # separately reported explainer line: edge-value gradient dvals[e] = <dS[row_e], X[col_e]>
-        ts = []
+        dv = torch.empty(nnz_local, dtype=torch.float32, device=dev)
+        Xv, dSv = eng.x_local_view(), eng.dS
         for _ in range(5):
+            ops.spmm_bwd_vals(g, dSv, Xv, out=dv)
+        ts = []
+        for _ in range(20):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); dv = ops.spmm_bwd_vals(g, dS, X_local); b.record()
+            a.record(); ops.spmm_bwd_vals(g, dSv, Xv, out=dv); b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        del dv
-        sd_ms = float(np.mean(ts[1:]))
+        del dv, Xv, dSv
+        sd_ms = float(np.median(ts))
         bv = nnz_local * (8 * D + 8 + 4)
-        sddmm = {"kernel": "sddmm (iddgcn_spmm_bwd_vals)", "ms": sd_ms, "bytes": bv, "GBps": bv / sd_ms / 1e6,
+        sddmm = {"kernel": "sddmm_stream_kernel (iddgcn_spmm_bwd_vals)", "ms": sd_ms, "ms_min": float(min(ts)),
+                 "ms_max": float(max(ts)), "iters": 20, "bytes": bv, "GBps": bv / sd_ms / 1e6,
                  "edges_per_s": nnz_local / (sd_ms * 1e-3)}
-    fwd_ms, bwd_ms = float(np.mean(kt["fwd"])), float(np.mean(kt["bwd"]))
-    bf, bb = algorithmic_bytes(nnz_local, n_rows, N_total, R, D)
+    fwd_ms, bwd_ms = float(np.median(kt["fwd"])), float(np.median(kt["bwd"]))
+    bf, bb = algorithmic_bytes(nnz_local, n_rows, N_total, R, Dc)
     peak, peak_src = hbm_peak()
     dom = "fwd" if fwd_ms >= bwd_ms else "bwd"
     dom_bytes, dom_ms = (bf, fwd_ms) if dom == "fwd" else (bb, bwd_ms)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-        traffic = tj.get(wl["name"], {}).get(dom)
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    if world == 1 and not wl.get("dim_override"):
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            traffic = tj.get(wl["name"], {}).get(dom)
+            if traffic is not None:
+                traffic_src = "static: ncu --set full capture of this kernel on this workload, committed in profiles/"
+        except Exception:
+            pass
     kname = "gather_rows_kernel" if os.environ.get("IDDGCN_SPMM_V1") == "1" else "stream_rows_kernel"
     roofline = {"bound": "hbm", "kernel": f"{kname} ({'iddgcn_spmm_fwd' if dom == 'fwd' else 'iddgcn_spmm_bwd_x'})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
+                "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "ms": dom_ms,
+                "per_rank_shape": {"rows": n_rows, "source_nodes": N_total, "edges": nnz_local, "feature_cols": Dc},
                 "fwd": {"ms": fwd_ms, "bytes": bf, "GBps": bf / fwd_ms / 1e6, "frac": bf / fwd_ms / 1e6 / peak},
                 "bwd": {"ms": bwd_ms, "bytes": bb, "GBps": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
                 "step_frac": (bf + bb) / (ms_per_step * 1e-3) / 1e9 / peak}
 
     # end-to-end through the C ABI with HOST buffers (pinned): H2D + fwd + bwd + D2H every step
     e2e = None
-    if world == 1:
-        Xh = X_local.cpu().pin_memory(); dSh = dS.cpu().pin_memory()
-        Sh = torch.empty((R, n_rows, D)).pin_memory(); dXh = torch.empty((N_total, D)).pin_memory()
-        del S, dX, X_local, dS
+    if args.no_e2e:
+        e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": True}
+    elif world == 1 and host_mem_short(4 * (2 * N_total * D + 2 * R * n_rows * D)):
+        e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "skipped": True,
+               "reason": "host RAM too small to pin the buffers of this workload: " + host_mem_short.last}
+    elif world == 1:
+        Xh = torch.empty((N_total, D), pin_memory=True); Xh.copy_(eng.x_local_view())
+        dSh = torch.empty((R, n_rows, D), pin_memory=True); dSh.copy_(eng.dS)
+        Sh = torch.empty((R, n_rows, D), pin_memory=True); dXh = torch.empty((N_total, D), pin_memory=True)
+        del eng, step                                 # the host entry point owns its device buffers
         torch.cuda.empty_cache()
         k2 = max(3, min(args.steps, 5))
         for _ in range(2):
@@ -399,36 +579,33 @@ def run_ours(args, wl):
         e2e = {"value": nnz_global / dt, "unit": "edges/s", "h2d_bytes_per_step": Xh.numel() * 4 + dSh.numel() * 4,
                "d2h_bytes_per_step": Sh.numel() * 4 + dXh.numel() * 4, "ms_per_step": dt * 1e3, "steps": k2,
                "launches_per_step": (_lib.launch_count() - l0) / k2,
+               "pcie_GBps_up+down": (Xh.numel() + dSh.numel() + Sh.numel() + dXh.numel()) * 4 / dt / 1e9,
                "api": "iddgcn_spmm_fwd_bwd_host (pinned host buffers in/out)"}
         del Xh, dSh, Sh, dXh
     else:
-        e2e = engine.e2e(args, nnz_global)
+        e2e = eng.e2e(args.steps, nnz_global)
+        eng.check_timeouts()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        if wl["per_rel"] <= 20_000_000 and not wl.get("zipf"):
-            # the very graph and inputs the GPU just ran, exported through the C ABI
-            struct = g.export()
-            cN, cn_rows, cnnz = N_total, n_rows, nnz_local
-            gen = torch.Generator().manual_seed(5)
-            cX = torch.rand((cN, D), generator=gen).numpy()
-            cdS = torch.randn((R * cn_rows, D), generator=gen).numpy()
-            sample = f"{wl['name']} (full workload, the graph the GPU ran): {cN} nodes, {cnnz} edges, 2 timed passes"
-        else:
-            struct, cN, cn_rows, cnnz, cX, cdS, sample = cpu_sample_inputs(wl)
-        cpu_baseline_run(struct, cN, cn_rows, R, D, cX, cdS, 1)
-        times, cores = cpu_baseline_run(struct, cN, cn_rows, R, D, cX, cdS, 2)
+        struct, cN, cnnz, cX, cdS, sample = cpu_sample_inputs(wl)
+        cpu_baseline_run(struct, cN, cN, R, D, cX, cdS, 1)
+        times, cores = cpu_baseline_run(struct, cN, cN, R, D, cX, cdS, 2)
         cpu = {"value": cnnz * len(times) / sum(times), "unit": "edges/s", "cores": cores, "kind": "port",
-               "sample": sample, "host_cpus": os.cpu_count()}
+               "sample": sample + ", 2 timed passes", "host_cpus": os.cpu_count()}
     if rank == 0:
         line = {
             "metric": "relational_spmm_fwd_bwd_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "nodes": N_total, "edges": nnz_global, "relations": R,
-                       "feature_dim": D, "rows_per_gpu": n_rows, "partition": f"dest-row blocks x{world}",
-                       "l2": "inputs larger than L2 (no flush needed)", "graph_build_s": build_s},
+                       "feature_dim": D, "rows_per_gpu": n_rows, "feature_cols_per_gpu": Dc,
+                       "partition": (f"{grid[0]} destination-row blocks x {grid[1]} feature-column groups; rank (pr,pc) "
+                                     f"holds X[rows_pr, cols_pc], dS/S[:, rows_pr, cols_pc], dX[rows_pr, cols_pc]"),
+                       "l2": "inputs larger than L2 (no flush needed)", "graph_build_s": build_s,
+                       "edge_recipe_s": gen_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity,
         }
         if comm is not None:
             line["comm"] = comm
@@ -446,13 +623,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (A/B runs only)")
+    ap.add_argument("--no-sddmm", action="store_true", help="skip the separately reported SDDMM line")
     ap.add_argument("--dim", type=int, default=0, help="override the feature width D of the workload (default 128)")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "nvls"],
-                    help="multi-GPU exchange: NCCL collectives or hand-written NVSwitch multicast kernels")
-    ap.add_argument("--mc-ctas", type=int, default=32, help="thread blocks of the multicast copy kernels")
-    ap.add_argument("--panels", type=int, default=2, help="column panels of the multi-GPU exchange pipeline")
+    ap.add_argument("--grid", default="auto", help="rank grid 'RxC': R destination-row blocks x C feature-column "
+                                                    "groups (auto: 1x2, 2x2, 2x4 at 2/4/8 GPUs)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="row exchange inside a column group: fused peer-memory kernels or NCCL collectives")
+    ap.add_argument("--check-rows", type=int, default=1_000_000,
+                    help="rows (over all ranks) of S and of dX compared with the CPU oracle after the timed region")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -461,13 +642,7 @@ def main():
     if args.dim:
         wl["D"] = args.dim
         wl["dim_override"] = True
-    wl["label"] = {
-        "c3": "synthetic 1M-node / 20M-edge 2-relation directed graph, D=128 (BASELINE configs[2]); "
-              "xP row-partitioned at --gpus P (configs[3] recipe, weak)",
-        "c4": "synthetic 20M-node / 200M-edge 2-relation graph, D=128, destination-row partitioned (configs[3])",
-        "small": "synthetic 100k-node / 2M-edge 2-relation graph, D=128 (smoke size)",
-        "c3zipf": "config-3 shape with Zipf(1.2) destination degrees (skewed variant, SURVEY 8d)",
-    }[args.workload]
+    wl["label"] = LABELS[args.workload]
     if wl.get("dim_override"):
         wl["label"] += f" [feature dim overridden to {wl['D']}]"
     if args.impl == "reference":

@@ -35,6 +35,15 @@ _SIGNATURES = {
     "iddgcn_spmm_fwd": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, vp, vp]),
     "iddgcn_spmm_bwd_x": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, vp, C.c_int, vp]),
     "iddgcn_spmm_bwd_vals": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int, vp, vp]),
+    "iddgcn_spmm_fwd_rows": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, vp, C.c_int64, C.c_int64, vp]),
+    "iddgcn_spmm_bwd_x_rows": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(vp),
+                                         C.c_int, vp]),
+    "iddgcn_spmm_prepare": (C.c_int, [vp, C.c_int64, vp]),
+    "iddgcn_peer_signal": (C.c_int, [C.POINTER(vp), C.c_int, C.c_uint32, vp]),
+    "iddgcn_peer_wait": (C.c_int, [C.POINTER(vp), C.c_int, C.c_uint32, C.c_int, vp, vp]),
+    "iddgcn_copy_async": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "iddgcn_copy2d_async": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int64, vp]),
+    "iddgcn_peer_push": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "iddgcn_edge_value_sums": (C.c_int, [vp, vp, C.c_int, vp, vp]),
     "iddgcn_spmm_fwd_bwd_host": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "iddgcn_spmm_fwd_dl": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),

@@ -182,7 +182,7 @@ static int graph_build_impl(const int64_t* triples_in, int64_t M, int on_device,
   const int64_t n_rows = row_hi - row_lo;
   KeyLayout L;
   L.bt = ceil_log2_u64((uint64_t)(N - 1));
-  L.bh = ceil_log2_u64((uint64_t)(n_rows - 1));
+  L.bh = n_rows > 0 ? ceil_log2_u64((uint64_t)(n_rows - 1)) : 1;   // an empty row block keeps no triple at all
   L.br = ceil_log2_u64((uint64_t)(R - 1));
   if (L.bt < 1) L.bt = 1;
   if (L.bh < 1) L.bh = 1;
@@ -335,8 +335,8 @@ static void graph_free(iddgcn_graph* g) {
   pool_free(g->block_edges);   // csr_col, csr_row, csc_row, csc_perm, bwd_src, bwd_perm likewise
   pool_free(g->heavy_fwd.rows); pool_free(g->heavy_fwd.segptr);
   pool_free(g->heavy_bwd.rows); pool_free(g->heavy_bwd.segptr);
-  cudaFree(g->heavy_ws);
-  cudaFree(g->host_ws);
+  pool_free(g->heavy_ws);
+  pool_free(g->host_ws);
   for (int i = 0; i < 3; ++i)
     if (g->host_streams[i]) cudaStreamDestroy(g->host_streams[i]);
   for (int i = 0; i < 16; ++i)
@@ -503,7 +503,9 @@ int iddgcn_graph_build(const int64_t* triples, int64_t M, int triples_on_device,
   *out = nullptr;
   IDD_CHECK(M >= 0 && (M == 0 || triples != nullptr), IDDGCN_EINVAL, "triples is NULL with M=%lld", (long long)M);
   IDD_CHECK(num_entities > 0 && num_relations > 0, IDDGCN_EINVAL, "num_entities and num_relations must be positive");
-  IDD_CHECK(row_lo >= 0 && row_lo < row_hi && row_hi <= num_entities, IDDGCN_EINVAL,
+  // row_lo == row_hi is a valid (empty) block: with N not divisible by the number of row blocks the trailing ranks of a
+  // partition own nothing, and they still have to take part in the exchange
+  IDD_CHECK(row_lo >= 0 && row_lo <= row_hi && row_hi <= num_entities, IDDGCN_EINVAL,
             "row block [%lld,%lld) is not inside [0,%lld)", (long long)row_lo, (long long)row_hi,
             (long long)num_entities);
   int ndev = 0;

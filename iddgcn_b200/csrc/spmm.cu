@@ -18,6 +18,25 @@ namespace iddgcn {
 
 constexpr int SPMM_THREADS = 256;
 
+// Extra addends of an output row: out[o] = gathered sum + Σ_j add.p[j][o].  n == 0: plain store; the classic
+// "accumulate" (out += ...) is add.p[0] == out.  The partitioned backward uses it to fold the partial dX rows that
+// peer GPUs pushed into this rank's stage buffers into the epilogue of the kernel that computes the rank's own
+// partial (fixed order: own partial, then peers in rank order), so the reduce-scatter needs no reduction pass.
+constexpr int MAX_ADD = 8;
+struct AddSrcs {
+  const float* p[MAX_ADD];
+  int n;
+};
+static inline AddSrcs add_none() { AddSrcs a{}; a.n = 0; return a; }
+static inline AddSrcs add_self(const float* out) { AddSrcs a{}; a.n = 1; a.p[0] = out; return a; }
+
+__device__ __forceinline__ void add_rows(float4& r, const AddSrcs& add, size_t vec_index) {
+  for (int j = 0; j < add.n; ++j) {
+    const float4 prev = *(reinterpret_cast<const float4*>(add.p[j]) + vec_index);
+    r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ float edge_weight(const float* __restrict__ vals, int e) {
   if (MODE == IDDGCN_VALS_ONES) return 1.0f;
@@ -36,7 +55,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     gather_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
                        const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
-                       int G, int64_t seg_stride, int64_t src_group_rows, int nvec /* D/4 */, int accumulate,
+                       int G, int64_t seg_stride, int64_t src_group_rows, int nvec /* D/4 */, AddSrcs add,
                        int heavy_t) {
   constexpr int SUBS = 32 / LPR;
   const int lane = threadIdx.x & 31;
@@ -104,10 +123,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     const int vi = l + c * LPR;
     if (vi < nvec) {
       float4 r = acc[c];
-      if (accumulate) {
-        const float4 prev = orow[vi];
-        r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
-      }
+      add_rows(r, add, (size_t)o * nvec + vi);
       st_stream_f4(orow + vi, r);
     }
   }
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__(TPB, MINB)
     stream_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
                        const float* __restrict__ src, float* __restrict__ out, int64_t row_begin, int64_t row_end,
-                       int nvec, int accumulate, int heavy_t) {
+                       int nvec, AddSrcs add, int heavy_t) {
   constexpr int SUBS = 32 / LPR;
   constexpr int SUB_SLAB = SLAB / SUBS;
   constexpr bool WEIGHTED = MODE != IDDGCN_VALS_ONES;
@@ -167,10 +183,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        if (accumulate) {
-          const float4 prev = *o;
-          r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
-        }
+        add_rows(r, add, (size_t)(r0 + row) * nvec + l);
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -229,10 +242,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        if (accumulate) {
-          const float4 prev = *o;
-          r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
-        }
+        add_rows(r, add, (size_t)(r0 + row) * nvec + l);
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 __global__ void __launch_bounds__(256)
     heavy_reduce_kernel(const int32_t* __restrict__ hub_rows, const int32_t* __restrict__ hub_segptr, int H,
                         const float* __restrict__ scratch, float* __restrict__ out, int64_t row_begin, int64_t row_end,
-                        int nvec, int accumulate) {
+                        int nvec, AddSrcs add) {
   const int h = blockIdx.x;
   const int64_t row = hub_rows[h];
   if (row < row_begin || row >= row_end) return;
@@ -398,10 +408,7 @@ __global__ void __launch_bounds__(256)
       const float4 p = s4[(size_t)sg * nvec + vi];
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
-    if (accumulate) {
-      const float4 prev = o4[vi];
-      acc.x += prev.x; acc.y += prev.y; acc.z += prev.z; acc.w += prev.w;
-    }
+    add_rows(acc, add, (size_t)row * nvec + vi);
     o4[vi] = acc;
   }
 }
@@ -509,6 +516,165 @@ __global__ void __launch_bounds__(SPMM_THREADS)
   sddmm_range<LPR, CH, U, MODE>(idx, vals, dS, X, dvals, o, beg, end, nvec, mask, l);
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2 SDDMM: the flat-edge-stream pattern of stream_rows_kernel applied to the edge-value gradient.
+//
+// A slice of LPR lanes owns a chunk of LPR consecutive CSR rows; the chunk's index range is staged in a shared-memory
+// slab and consumed in batches of U edges regardless of row boundaries.  Per batch the slice first walks the row ends
+// (registers + shuffles only) to learn which edges start a new row, then issues U independent 128-bit gathers of
+// X[col] together with the (predicated) loads of the dS rows that begin inside the batch — an edge that continues the
+// previous edge's row reuses its register copy — so a row switch costs no dependent memory latency.  The U dot
+// products are reduced with a transpose reduction (U/2 + U/4 + ... shuffles instead of U·log2(LPR)) that leaves edge
+// i of the batch in lane i·(LPR/U), and those lanes write U consecutive floats (one 32-byte sector).
+//   dvals[e] = <dS[row(e), :], X[idx[e], :]>  (· σ'(vals[e]) in SIGMOID mode, staged once per edge with the indices)
+template <int LPR, int NV, int OFF>
+struct SliceReduce {
+  static __device__ __forceinline__ void run(float* v, int l, unsigned mask) {
+    if constexpr (OFF >= 1) {
+      if constexpr (NV > 1) {
+        constexpr int H = NV / 2;
+        const bool hi = (l & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+          const float send = hi ? v[i] : v[i + H];
+          const float keep = hi ? v[i + H] : v[i];
+          v[i] = keep + __shfl_xor_sync(mask, send, OFF, LPR);
+        }
+        SliceReduce<LPR, H, OFF / 2>::run(v, l, mask);
+      } else {
+        v[0] += __shfl_xor_sync(mask, v[0], OFF, LPR);
+        SliceReduce<LPR, 1, OFF / 2>::run(v, l, mask);
+      }
+    }
+  }
+};
+
+template <int LPR, int U, int MODE, bool HUBS, int TPB = SPMM_THREADS, int MINB = 3>
+__global__ void __launch_bounds__(TPB, MINB)
+    sddmm_stream_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                        const float* __restrict__ vals, const float* __restrict__ dS, const float* __restrict__ X,
+                        float* __restrict__ dvals, int64_t num_rows, int nvec, int heavy_t) {
+  constexpr int SUBS = 32 / LPR;
+  constexpr int SUB_SLAB = SLAB / SUBS;
+  constexpr bool SIG = MODE == IDDGCN_VALS_SIGMOID;
+  constexpr int KEEP = (U > LPR) ? U / LPR : 1;          // results left per lane by the transpose reduction
+  constexpr int STRIDE = (LPR > U) ? LPR / U : 1;        // lane spacing of the result holders
+  __shared__ int32_t s_idx[TPB / 32][SLAB];
+  __shared__ float s_w[SIG ? TPB / 32 : 1][SIG ? SLAB : 1];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * (TPB / 32) + warp) * SUBS + sub;
+  const int64_t r0 = chunk * LPR;
+  if (r0 >= num_rows) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int nrows = (num_rows - r0 < LPR) ? (int)(num_rows - r0) : LPR;
+  int32_t* const sl_idx = &s_idx[warp][sub * SUB_SLAB];
+  float* const sl_w = SIG ? &s_w[warp][sub * SUB_SLAB] : nullptr;
+
+  const int chunk_beg = ld_stream_i32(ptr + r0);
+  const int my_end = (l < nrows) ? ld_stream_i32(ptr + r0 + l + 1) : 0x7fffffff;
+  const int chunk_end = __shfl_sync(mask, my_end, nrows - 1, LPR);
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+  const float4* __restrict__ G4 = reinterpret_cast<const float4*>(dS) + (size_t)r0 * nvec;
+  const bool live = l < nvec;
+
+  int row = 0, row_beg = chunk_beg;
+  int cur_end = __shfl_sync(mask, my_end, 0, LPR);
+  bool heavy_cur = HUBS && (cur_end - row_beg > heavy_t);
+  bool fresh = true;                       // the first edge of the next batch starts a row not yet loaded
+  int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
+  float4 g_carry = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  while (true) {
+    // skip finished / empty rows and hub rows (those are written by sddmm_hub_kernel)
+    while (row < nrows && (pos == cur_end || heavy_cur)) {
+      pos = cur_end;
+      row_beg = cur_end;
+      ++row;
+      heavy_cur = false;
+      fresh = true;
+      if (row < nrows) {
+        cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
+        heavy_cur = HUBS && (cur_end - row_beg > heavy_t);
+      }
+    }
+    if (row >= nrows) break;
+    if (pos + U > slab_hi && slab_hi < chunk_end) {  // refill the slab starting at the current position
+      __syncwarp(mask);
+      slab_lo = pos;
+      slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
+      for (int q = l; q < slab_hi - slab_lo; q += LPR) {
+        const int e = slab_lo + q;
+        sl_idx[q] = ld_stream_i32(idx + e);
+        if (SIG) {
+          const float sg = sigmoidf_(__ldg(vals + e));
+          sl_w[q] = sg * (1.0f - sg);
+        }
+      }
+      __syncwarp(mask);
+    }
+    int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
+    float4 v[U], gs[U];
+    // issue phase: row walk in registers, then every load of the batch
+    int r = row, ce = cur_end, rb = row_beg;
+    bool hv = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool nw = (u == 0) ? fresh : false;
+      if (u < n) {
+        while (ce == pos + u) {          // edge u starts a later row (rows in between are empty)
+          rb = ce;
+          ++r;
+          ce = (r < nrows) ? __shfl_sync(mask, my_end, r & (LPR - 1), LPR) : 0x7fffffff;
+          nw = true;
+        }
+        if (HUBS && nw && u > 0 && ce - rb > heavy_t) {  // a hub row starts here: end the batch before it
+          n = u;
+          hv = true;
+        }
+      }
+      if (u < n) {
+        const int sidx = sl_idx[pos + u - slab_lo];
+        v[u] = live ? __ldg(X4 + (size_t)sidx * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nw) gs[u] = live ? ld_stream_f4(G4 + (size_t)r * nvec + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+        else gs[u] = (u == 0) ? g_carry : gs[u > 0 ? u - 1 : 0];
+      } else {
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gs[u] = (u == 0) ? g_carry : gs[u > 0 ? u - 1 : 0];
+      }
+    }
+    float p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float a = gs[u].x * v[u].x;
+      a = fmaf(gs[u].y, v[u].y, a);
+      a = fmaf(gs[u].z, v[u].z, a);
+      a = fmaf(gs[u].w, v[u].w, a);
+      p[u] = a;
+    }
+    SliceReduce<LPR, U, LPR / 2>::run(p, l, mask);
+    if ((l % STRIDE) == 0) {
+      const int base = (l / STRIDE) * KEEP;
+#pragma unroll
+      for (int i = 0; i < KEEP; ++i) {
+        if (base + i < n) {
+          float out = p[i];
+          if (SIG) out *= sl_w[pos + base + i - slab_lo];
+          dvals[pos + base + i] = out;
+        }
+      }
+    }
+    g_carry = gs[U - 1];
+    fresh = false;
+    pos += n;
+    row = r; cur_end = ce; row_beg = rb;
+    heavy_cur = hv;
+    if (hv) fresh = true;
+  }
+}
+
 // one block per relation, fixed-order reduction
 template <int MODE>
 __global__ void __launch_bounds__(256) edge_value_sums_kernel(const int32_t* __restrict__ rowptr, int64_t n_rows,
@@ -533,7 +699,7 @@ __global__ void __launch_bounds__(256) edge_value_sums_kernel(const int32_t* __r
 // ---------------------------------------------------------------------------
 struct GatherArgs {
   const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
-  int64_t row_begin, row_end; int G; int64_t seg_stride, src_group_rows; int nvec; int accumulate; int heavy_t;
+  int64_t row_begin, row_end; int G; int64_t seg_stride, src_group_rows; int nvec; AddSrcs add; int heavy_t;
 };
 
 template <int LPR, int CH, int U, bool USE_PERM>
@@ -546,7 +712,7 @@ static int launch_gather_mode(const GatherArgs& a, int mode, cudaStream_t st) {
 #define IDD_GATHER(MODE_)                                                                                        \
   gather_rows_kernel<LPR, CH, U, MODE_, USE_PERM><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(                    \
       a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.G, a.seg_stride, a.src_group_rows,  \
-      a.nvec, a.accumulate, a.heavy_t)
+      a.nvec, a.add, a.heavy_t)
   if (mode == IDDGCN_VALS_ONES) IDD_GATHER(IDDGCN_VALS_ONES);
   else if (mode == IDDGCN_VALS_EXPLICIT) IDD_GATHER(IDDGCN_VALS_EXPLICIT);
   else IDD_GATHER(IDDGCN_VALS_SIGMOID);
@@ -601,7 +767,7 @@ static int launch_sddmm_mode(const iddgcn_graph* g, const float* dS, const float
 
 struct StreamArgs {
   const int32_t* ptr; const int32_t* idx; const int32_t* perm; const float* vals; const float* src; float* out;
-  int64_t row_begin, row_end; int nvec; int accumulate; int heavy_t;
+  int64_t row_begin, row_end; int nvec; AddSrcs add; int heavy_t;
 };
 
 template <int LPR, bool USE_PERM>
@@ -615,10 +781,10 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   do {                                                                                                        \
     if (a.heavy_t == 0x7fffffff)                                                                              \
       stream_rows_kernel<LPR, 8, MODE_, USE_PERM, false><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(          \
-          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t); \
+          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t); \
     else                                                                                                      \
       stream_rows_kernel<LPR, 8, MODE_, USE_PERM, true><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(           \
-          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t); \
+          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t); \
   } while (0)
   // IDDGCN_TUNE=<k>: launch-shape variants of the headline instantiation (D=128, unweighted, no hub rows) for A/B runs
   if (LPR == 32 && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff) {
@@ -629,7 +795,7 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
       do {                                                                                                          \
         const int64_t nb = (rows + (TPB_ / 32) * 32 - 1) / ((TPB_ / 32) * 32);                                      \
         stream_rows_kernel<32, U_, IDDGCN_VALS_ONES, USE_PERM, false, TPB_, MINB_, NA_><<<(unsigned)nb, TPB_, 0, st>>>( \
-            a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.accumulate, a.heavy_t);   \
+            a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t);   \
       } while (0)
       switch (k) {
         case 1: IDD_TUNE(8, 256, 4, true); break;
@@ -690,14 +856,23 @@ static int check_common(const iddgcn_graph* g, int64_t D, const float* vals, int
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- hub-row split pass ---------------------------------------------------------------------
-static int ensure_heavy_ws(const iddgcn_graph* g, int total_segs, int64_t D) {
+// The workspace of the split pass ([total_segs, D] partial sums) belongs to the graph handle and comes from the pool.
+// It is sized by iddgcn_spmm_prepare (called by the model before it captures its train step) or grown here on first
+// use; growing is refused while the stream is being captured (an allocation would invalidate the capture).
+static int ensure_heavy_ws(const iddgcn_graph* g, int total_segs, int64_t D, cudaStream_t st) {
   const size_t need = (size_t)total_segs * (size_t)D;
   if (need <= g->heavy_ws_elems) return IDDGCN_OK;
-  cudaFree(g->heavy_ws);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+    set_error("hub-row workspace (%zu floats) is not allocated and the stream is being captured: call "
+              "iddgcn_spmm_prepare(graph, D) before the capture", need);
+    return IDDGCN_EINVAL;
+  }
+  if (g->heavy_ws) pool_free(g->heavy_ws);
   g->heavy_ws = nullptr;
   g->heavy_ws_elems = 0;
-  IDD_CUDA(cudaMalloc((void**)&g->heavy_ws, need * sizeof(float)));   // fails inside a stream capture: call
-  g->heavy_ws_elems = need;                                            // iddgcn_spmm_* once before capturing
+  IDD_CUDA(pool_alloc((void**)&g->heavy_ws, need * sizeof(float)));
+  g->heavy_ws_elems = need;
   return IDDGCN_OK;
 }
 
@@ -721,56 +896,117 @@ static int launch_heavy_mode(const iddgcn_graph::HeavyList& hl, const int32_t* p
 template <bool USE_PERM>
 static int heavy_pass(const iddgcn_graph* g, const iddgcn_graph::HeavyList& hl, const int32_t* ptr,
                       const int32_t* idx, const int32_t* perm, const float* vals, int mode, const float* src,
-                      float* out, int64_t row_begin, int64_t row_end, int64_t D, int accumulate, cudaStream_t st) {
+                      float* out, int64_t row_begin, int64_t row_end, int64_t D, const AddSrcs& add, cudaStream_t st) {
   if (hl.H == 0) return IDDGCN_OK;
-  IDD_TRY(ensure_heavy_ws(g, hl.total_segs, D));
+  IDD_TRY(ensure_heavy_ws(g, hl.total_segs, D, st));
   const int nvec = (int)(D / 4);
   if (nvec <= 8) IDD_TRY((launch_heavy_mode<8, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
   else if (nvec <= 16) IDD_TRY((launch_heavy_mode<16, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
   else if (nvec <= 32) IDD_TRY((launch_heavy_mode<32, 1, 8, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
   else if (nvec <= 64) IDD_TRY((launch_heavy_mode<32, 2, 4, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
   else IDD_TRY((launch_heavy_mode<32, 4, 2, USE_PERM>(hl, ptr, idx, perm, vals, mode, src, g->heavy_ws, nvec, st)));
-  heavy_reduce_kernel<<<hl.H, 128, 0, st>>>(hl.rows, hl.segptr, hl.H, g->heavy_ws, out, row_begin, row_end, nvec,
-                                            accumulate);
+  heavy_reduce_kernel<<<hl.H, 128, 0, st>>>(hl.rows, hl.segptr, hl.H, g->heavy_ws, out, row_begin, row_end, nvec, add);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }
 
-// Both directions are the same generic gather  out[o] = Σ_{e in ptr[o]..ptr[o+1]} w(e)·src[idx[e]] :
+// Both directions are the same generic gather  out[o] = Σ_{e in ptr[o]..ptr[o+1]} w(e)·src[idx[e]] (+ Σ_j add_j[o]):
 //   forward  on (csr_rowptr, csr_col)            over R·n_rows rows, weight index e
 //   backward on (bwd_rowptr, bwd_src, bwd_perm)  over N rows (node-major CSC view), weight index perm[e]
+// `out` and the addends are indexed by the GLOBAL row id o (callers that hold only the rows of a range pass pointers
+// biased by -row_begin·D).
 template <bool USE_PERM>
 static int generic_gather(const iddgcn_graph* g, const iddgcn_graph::HeavyList& hl, const int32_t* ptr,
                           const int32_t* idx, const int32_t* perm, int64_t total_rows, const float* vals, int mode,
-                          const float* src, float* out, int64_t D, int accumulate, int64_t row_begin, int64_t row_end,
-                          cudaStream_t st) {
+                          const float* src, float* out, int64_t D, const AddSrcs& add, int64_t row_begin,
+                          int64_t row_end, cudaStream_t st) {
   const int heavy_t = hl.H > 0 ? HEAVY_EDGES : 0x7fffffff;
   if (D <= 128 && !use_v1(total_rows)) {
-    StreamArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, (int)(D / 4), accumulate, heavy_t};
+    StreamArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, (int)(D / 4), add, heavy_t};
     IDD_TRY(launch_stream<USE_PERM>(a, mode, st));
   } else {
-    GatherArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, 1, 0, 0, (int)(D / 4), accumulate, heavy_t};
+    GatherArgs a{ptr, idx, perm, vals, src, out, row_begin, row_end, 1, 0, 0, (int)(D / 4), add, heavy_t};
     IDD_TRY(launch_gather<USE_PERM>(a, mode, st));
   }
-  return heavy_pass<USE_PERM>(g, hl, ptr, idx, perm, vals, mode, src, out, row_begin, row_end, D, accumulate, st);
+  return heavy_pass<USE_PERM>(g, hl, ptr, idx, perm, vals, mode, src, out, row_begin, row_end, D, add, st);
 }
 
 int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float* vals, int mode, float* S,
                    int64_t row_begin, int64_t row_end, cudaStream_t st) {
   return generic_gather<false>(g, g->heavy_fwd, g->csr_rowptr, g->csr_col, nullptr, (int64_t)g->R * g->n_rows, vals,
-                               mode, X, S, D, 0, row_begin, row_end, st);
+                               mode, X, S, D, add_none(), row_begin, row_end, st);
+}
+
+static int spmm_bwd_x_add(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
+                          const AddSrcs& add, int64_t row_begin, int64_t row_end, cudaStream_t st) {
+  return generic_gather<true>(g, g->heavy_bwd, g->bwd_rowptr, g->bwd_src, g->bwd_perm, g->N, vals, mode, dS, dX, D,
+                              add, row_begin, row_end, st);
 }
 
 int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
                      int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st) {
-  return generic_gather<true>(g, g->heavy_bwd, g->bwd_rowptr, g->bwd_src, g->bwd_perm, g->N, vals, mode, dS, dX, D,
-                              accumulate, row_begin, row_end, st);
+  return spmm_bwd_x_add(g, dS, D, vals, mode, dX, accumulate ? add_self(dX) : add_none(), row_begin, row_end, st);
+}
+
+int spmm_prepare(const iddgcn_graph* g, int64_t D, cudaStream_t st) {
+  const int segs = g->heavy_fwd.total_segs > g->heavy_bwd.total_segs ? g->heavy_fwd.total_segs : g->heavy_bwd.total_segs;
+  if (segs == 0) return IDDGCN_OK;
+  return ensure_heavy_ws(g, segs, D, st);
+}
+
+// v2 (flat edge stream) for graphs large enough to fill the machine with 32-row chunks, v1 (row at a time) otherwise
+template <int LPR, int U, int MINB>
+static int launch_sddmm_stream(const iddgcn_graph* g, const float* dS, const float* X, const float* vals, int mode,
+                               float* dvals, int nvec, cudaStream_t st) {
+  const int64_t rows = (int64_t)g->R * g->n_rows;
+  constexpr int rows_per_block = (SPMM_THREADS / 32) * 32;
+  const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
+  IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
+  const iddgcn_graph::HeavyList& hl = g->heavy_fwd;
+  const int heavy_t = hl.H > 0 ? HEAVY_EDGES : 0x7fffffff;
+#define IDD_SDDMM(MODE_, HUBS_)                                                                              \
+  sddmm_stream_kernel<LPR, U, MODE_, HUBS_, SPMM_THREADS, MINB><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>( \
+      g->csr_rowptr, g->csr_col, vals, dS, X, dvals, rows, nvec, heavy_t)
+  if (mode == IDDGCN_VALS_SIGMOID) {
+    if (hl.H) IDD_SDDMM(IDDGCN_VALS_SIGMOID, true); else IDD_SDDMM(IDDGCN_VALS_SIGMOID, false);
+  } else {
+    if (hl.H) IDD_SDDMM(IDDGCN_VALS_EXPLICIT, true); else IDD_SDDMM(IDDGCN_VALS_EXPLICIT, false);
+  }
+#undef IDD_SDDMM
+  IDD_LAUNCH_CHECK();
+  if (hl.H) {
+    constexpr int per_block = (SPMM_THREADS / 32) * (32 / LPR);
+    const unsigned hblocks = (unsigned)((hl.total_segs + per_block - 1) / per_block);
+    if (mode == IDDGCN_VALS_SIGMOID)
+      sddmm_hub_kernel<LPR, 1, 8, IDDGCN_VALS_SIGMOID><<<hblocks, SPMM_THREADS, 0, st>>>(
+          g->csr_rowptr, g->csr_col, vals, dS, X, dvals, hl.rows, hl.segptr, hl.H, hl.total_segs, nvec);
+    else
+      sddmm_hub_kernel<LPR, 1, 8, IDDGCN_VALS_EXPLICIT><<<hblocks, SPMM_THREADS, 0, st>>>(
+          g->csr_rowptr, g->csr_col, vals, dS, X, dvals, hl.rows, hl.segptr, hl.H, hl.total_segs, nvec);
+    IDD_LAUNCH_CHECK();
+  }
+  return IDDGCN_OK;
 }
 
 int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64_t D, const float* vals, int mode,
                    float* dvals, cudaStream_t st) {
   if (g->nnz == 0) return IDDGCN_OK;
   const int nvec = (int)(D / 4);
+  if (D <= 128 && !use_v1((int64_t)g->R * g->n_rows)) {
+    if (nvec <= 4) return launch_sddmm_stream<4, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 8) return launch_sddmm_stream<8, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 16) return launch_sddmm_stream<16, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (const char* tv = getenv("IDDGCN_SDDMM_TUNE")) {   // launch-shape variants of the D=128 instantiation (A/B runs)
+      switch (atoi(tv)) {
+        case 1: return launch_sddmm_stream<32, 8, 2>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 2: return launch_sddmm_stream<32, 4, 4>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 3: return launch_sddmm_stream<32, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 4: return launch_sddmm_stream<32, 8, 4>(g, dS, X, vals, mode, dvals, nvec, st);
+        default: break;
+      }
+    }
+    return launch_sddmm_stream<32, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+  }
   if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
   if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
   if (nvec <= 32) return launch_sddmm_mode<32, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
@@ -789,6 +1025,7 @@ extern "C" {
 int iddgcn_spmm_fwd(const iddgcn_graph_t* g, const float* X, int64_t D, const float* vals, int vals_mode, float* S,
                     void* stream) {
   IDD_TRY(check_common(g, D, vals, vals_mode));
+  if (g->n_rows == 0) return IDDGCN_OK;   // empty row block of a partition: nothing to write
   IDD_CHECK(X && S, IDDGCN_EINVAL, "X or S is NULL");
   IDD_CHECK(aligned16(X) && aligned16(S), IDDGCN_EINVAL, "X and S must be 16-byte aligned");
   return spmm_fwd_range(g, X, D, vals, vals_mode, S, 0, (int64_t)g->R * g->n_rows, (cudaStream_t)stream);
@@ -797,9 +1034,47 @@ int iddgcn_spmm_fwd(const iddgcn_graph_t* g, const float* X, int64_t D, const fl
 int iddgcn_spmm_bwd_x(const iddgcn_graph_t* g, const float* dS, int64_t D, const float* vals, int vals_mode,
                       float* dX, int accumulate, void* stream) {
   IDD_TRY(check_common(g, D, vals, vals_mode));
-  IDD_CHECK(dS && dX, IDDGCN_EINVAL, "dS or dX is NULL");
+  IDD_CHECK((dS || g->nnz == 0) && dX, IDDGCN_EINVAL, "dS or dX is NULL");   // an empty row block has no dS rows
   IDD_CHECK(aligned16(dS) && aligned16(dX), IDDGCN_EINVAL, "dS and dX must be 16-byte aligned");
   return spmm_bwd_x_range(g, dS, D, vals, vals_mode, dX, accumulate, 0, g->N, (cudaStream_t)stream);
+}
+
+int iddgcn_spmm_prepare(const iddgcn_graph_t* g, int64_t D, void* stream) {
+  IDD_TRY(check_common(g, D, nullptr, IDDGCN_VALS_ONES));
+  return spmm_prepare(g, D, (cudaStream_t)stream);
+}
+
+int iddgcn_spmm_fwd_rows(const iddgcn_graph_t* g, const float* X, int64_t D, const float* vals, int vals_mode,
+                         float* S_rows, int64_t row_begin, int64_t row_end, void* stream) {
+  IDD_TRY(check_common(g, D, vals, vals_mode));
+  if (row_begin == row_end) return IDDGCN_OK;
+  IDD_CHECK(X && S_rows, IDDGCN_EINVAL, "X or S_rows is NULL");
+  IDD_CHECK(aligned16(X) && aligned16(S_rows), IDDGCN_EINVAL, "X and S_rows must be 16-byte aligned");
+  IDD_CHECK(0 <= row_begin && row_begin <= row_end && row_end <= (int64_t)g->R * g->n_rows, IDDGCN_EINVAL,
+            "row range [%lld, %lld) outside [0, R*n_rows)", (long long)row_begin, (long long)row_end);
+  return spmm_fwd_range(g, X, D, vals, vals_mode, S_rows - (size_t)row_begin * D, row_begin, row_end,
+                        (cudaStream_t)stream);
+}
+
+int iddgcn_spmm_bwd_x_rows(const iddgcn_graph_t* g, const float* dS, int64_t D, const float* vals, int vals_mode,
+                           float* dX_rows, int64_t node_begin, int64_t node_end, const float* const* addends,
+                           int n_addends, void* stream) {
+  IDD_TRY(check_common(g, D, vals, vals_mode));
+  if (node_begin == node_end) return IDDGCN_OK;
+  IDD_CHECK((dS || g->nnz == 0) && dX_rows, IDDGCN_EINVAL, "dS or dX_rows is NULL");
+  IDD_CHECK(aligned16(dS) && aligned16(dX_rows), IDDGCN_EINVAL, "dS and dX_rows must be 16-byte aligned");
+  IDD_CHECK(0 <= node_begin && node_begin <= node_end && node_end <= g->N, IDDGCN_EINVAL,
+            "node range [%lld, %lld) outside [0, N)", (long long)node_begin, (long long)node_end);
+  IDD_CHECK(n_addends >= 0 && n_addends <= MAX_ADD && (n_addends == 0 || addends != nullptr), IDDGCN_EINVAL,
+            "n_addends must be in [0, %d]", MAX_ADD);
+  AddSrcs add = add_none();
+  for (int j = 0; j < n_addends; ++j) {
+    IDD_CHECK(addends[j] != nullptr && aligned16(addends[j]), IDDGCN_EINVAL, "addend %d is NULL or misaligned", j);
+    add.p[j] = addends[j] - (size_t)node_begin * D;
+  }
+  add.n = n_addends;
+  return spmm_bwd_x_add(g, dS, D, vals, vals_mode, dX_rows - (size_t)node_begin * D, add, node_begin, node_end,
+                        (cudaStream_t)stream);
 }
 
 int iddgcn_spmm_bwd_vals(const iddgcn_graph_t* g, const float* dS, const float* X, int64_t D, const float* vals,
@@ -852,10 +1127,10 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
   const size_t xN = (size_t)g->N * D, sN = (size_t)srows * D;
   const size_t need = 2 * xN + 2 * sN;
   if (g->host_ws_elems < need) {
-    cudaFree(g->host_ws);
+    if (g->host_ws) pool_free(g->host_ws);
     g->host_ws = nullptr;
     g->host_ws_elems = 0;
-    IDD_CUDA(cudaMalloc((void**)&g->host_ws, need * sizeof(float)));
+    IDD_CUDA(pool_alloc((void**)&g->host_ws, need * sizeof(float)));
     g->host_ws_elems = need;
   }
   float* X_dev = g->host_ws;                 // [P][N][Dp]

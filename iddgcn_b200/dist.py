@@ -1,269 +1,440 @@
-"""Destination-row partitioned relational SpMM over the GPUs of one NVSwitch box (BASELINE configs[3]).
+"""Grid-partitioned relational SpMM over the GPUs of one NVSwitch box (BASELINE configs[3]).
 
-Rank p owns destination rows [p·B, (p+1)·B) of every relation (its Graph is built with row_block=...), the matching
-rows of S / dS, and the same block of the features X.  One exchange per direction:
+The ranks form a P_r x P_c grid.  Rank (pr, pc) owns
 
-    forward :  all-gather the feature blocks        -> X_full          -> S_local  = A_local · X_full
-    backward:  dX_partial = Σ_r A_local,rᵀ · dS_local -> reduce-scatter -> dX_local
+    * destination rows [pr·B, (pr+1)·B) of every relation (its Graph is built with row_block=...),
+    * feature columns  [pc·Dc, (pc+1)·Dc),  Dc = D / P_c,
 
-The feature dimension is cut into `panels` column panels (layout [panel][row][D/panels], each panel a compact
-matrix) so that NCCL moves panel c+1 over NVLink while the gather kernel works on panel c: both collectives are
-issued asynchronously on NCCL's stream and only their completion events are awaited on the compute stream.
-`torch.distributed` is plumbing; the SpMM kernels are the hand-written ones behind the C ABI.
+i.e. the blocks X[rows_pr, cols_pc], dS[:, rows_pr, cols_pc] and the outputs S[:, rows_pr, cols_pc],
+dX[rows_pr, cols_pc].  An SpMM is independent per feature column, so ranks that differ in pc never talk; the P_r
+ranks of one column group exchange rows:
 
-The local compute is injected (`fwd_fn` / `bwd_fn`) so that the partition / collective logic can be exercised by
-world_size-2 gloo tests on the CPU; the default functions call the CUDA kernels and there is no CPU fallback here.
+    forward :  all-gather the X blocks of the group        -> X_full[N, Dc]   -> S_local  = A_local · X_full
+    backward:  dX_partial = Σ_r A_local,rᵀ · dS_local [N, Dc]  -> reduce-scatter over the group -> dX_local
+
+Per rank the exchange moves (P_r-1)/P_r · N · 4·D/P_c bytes each way: 8.96 GB at 8x1 on the 20M-node graph, 1.28 GB at
+2x4, nothing at 1xP.  P_c = 1 is the plain destination-row partition; P_r = 1 replicates the graph and splits only
+the feature columns.
+
+Exchange "p2p" (default, CUDA): no collective call on the data path.
+    * reduce-scatter: FUSED into the backward kernel.  The kernel is launched per owner block; for a peer's block its
+      output pointer is that peer's stage buffer (NVLink peer stores, the partial rows travel while the kernel runs);
+      for the rank's own block the kernel's epilogue adds the partials the peers pushed (fixed order -> reproducible).
+    * all-gather: each rank's copy engines push its X block into every peer's X_full on a side stream.
+    * ordering: 32-bit epoch flags in symmetric memory (iddgcn_peer_signal / iddgcn_peer_wait), no host barrier.
+  torch.distributed._symmetric_memory only allocates and maps the buffers (plumbing).
+Exchange "nccl": all_gather_into_tensor / reduce_scatter_tensor inside the column group (the baseline; also the path
+the world_size-2 gloo tests exercise on the CPU with injected compute).
+
+The local compute is injected (`fwd_fn` / `bwd_fn`) only by those CPU tests; the default functions call the CUDA kernels
+and there is no CPU fallback here.
 """
 from __future__ import annotations
 
+import ctypes as C
 import time
 
 import torch
 import torch.distributed as dist
 
+DEFAULT_GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+K_DONE, K_AG, K_PART = 0, 1, 2          # flag kinds
+SLOTS = 8                               # flag slots per kind (max ranks in a column group)
+
 
 def row_block(rank: int, world: int, n_total: int) -> tuple[int, int, int]:
-    """(lo, hi, block) — equal contiguous destination-row blocks, the last one possibly short."""
+    """(lo, hi, block) — equal contiguous destination-row blocks, the last ones possibly short or empty."""
     block = (n_total + world - 1) // world
     lo = min(rank * block, n_total)
     return lo, min(lo + block, n_total), block
 
 
-def panelize(x: torch.Tensor, panels: int) -> torch.Tensor:
-    """[..., n, D] row-major -> [panels, ..., n, D/panels] (each panel compact)."""
-    *lead, n, D = x.shape
-    if D % panels:
-        raise ValueError(f"D={D} is not divisible by panels={panels}")
-    return x.reshape(*lead, n, panels, D // panels).movedim(-2, 0).contiguous()
+def parse_grid(spec, world: int, D: int) -> tuple[int, int]:
+    """'RxC' / (R, C) / None -> (P_r, P_c) with P_r·P_c == world and D divisible into P_c column groups of 4k floats."""
+    if spec is None or spec == "auto":
+        pr, pc = DEFAULT_GRIDS.get(world, (world, 1))
+        while pc > 1 and D % (4 * pc):
+            pc //= 2
+            pr = world // pc
+    elif isinstance(spec, str):
+        pr, pc = (int(x) for x in spec.lower().split("x"))
+    else:
+        pr, pc = int(spec[0]), int(spec[1])
+    if pr * pc != world:
+        raise ValueError(f"grid {pr}x{pc} does not match world size {world}")
+    if D % pc or (D // pc) % 4:
+        raise ValueError(f"D={D} does not split into {pc} column groups whose width is a multiple of 4")
+    return pr, pc
 
 
-def unpanelize(xp: torch.Tensor) -> torch.Tensor:
-    """Inverse of panelize."""
-    panels = xp.shape[0]
-    y = xp.movedim(0, -2)
-    *lead, n, p, dc = y.shape
-    return y.reshape(*lead, n, p * dc).contiguous()
+def grid_coords(rank: int, grid: tuple[int, int]) -> tuple[int, int]:
+    """rank -> (pr, pc); ranks of one column group are pc, pc+P_c, pc+2·P_c, ..."""
+    return rank // grid[1], rank % grid[1]
 
 
-def _all_gather(out: torch.Tensor, inp: torch.Tensor, async_op: bool, group=None):
-    return dist.all_gather_into_tensor(out, inp, group=group, async_op=async_op)
-
-
-def _reduce_scatter(out: torch.Tensor, inp: torch.Tensor, rank: int, async_op: bool, group=None):
+def _reduce_scatter(out, inp, index, group):
     if dist.get_backend() == "nccl":
-        return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group, async_op=True)
     # host-logic path for the gloo tests (no reduce-scatter there): all-reduce, keep this rank's block
     dist.all_reduce(inp, op=dist.ReduceOp.SUM, group=group)
     n = out.shape[0]
-    out.copy_(inp[rank * n:(rank + 1) * n])
+    out.copy_(inp[index * n:(index + 1) * n])
     return None
 
 
-class _NvlsBuffers:
-    """Symmetric (multicast-mapped) buffers + the hand-written multimem kernels of csrc/nvls.cu.
-
-    torch.distributed._symmetric_memory is the plumbing (cuMulticast* object, handle exchange, signal-pad barriers);
-    the data movement is ours: `iddgcn_mc_store` (all-gather leg, multimem.st) and `iddgcn_mc_reduce_load`
-    (reduce-scatter leg, multimem.ld_reduce.add)."""
-
-    def __init__(self, shape, device, group):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.full = symm_mem.empty(*shape, dtype=torch.float32, device=device)
-        self.partial = symm_mem.empty(*shape, dtype=torch.float32, device=device)
-        self.h_full = symm_mem.rendezvous(self.full, group)
-        self.h_part = symm_mem.rendezvous(self.partial, group)
-        self.mc_full = int(self.h_full.multicast_ptr)
-        self.mc_part = int(self.h_part.multicast_ptr)
-        if not self.mc_full or not self.mc_part:
-            raise RuntimeError("NVLS multicast is not available on this system")
-        self.s_ag = torch.cuda.Stream(device=device, priority=-1)
-        self.s_rs = torch.cuda.Stream(device=device, priority=-1)
-
-
-class PartitionedSpMM:
-    def __init__(self, graph, D: int, world: int, rank: int, block: int, *, panels: int = 4, fwd_fn=None,
-                 bwd_fn=None, device=None, ag_group=None, rs_group=None, exchange: str = "nccl", mc_ctas: int = 32):
-        if D % panels or (D // panels) % 4:
-            raise ValueError(f"D={D} must split into {panels} panels whose width is a multiple of 4")
-        self.g, self.D, self.world, self.rank, self.block, self.panels = graph, D, world, rank, block, panels
-        self.Dc = D // panels
-        # two communicators (two NCCL streams): the all-gather is receive-heavy and the reduce-scatter send-heavy, so
-        # running them concurrently keeps both NVLink directions busy
-        self.ag_group, self.rs_group = ag_group, rs_group
-        self.R = graph.R
-        self.n_rows = graph.n_rows
-        self.N_pad = block * world            # all-gather needs equal blocks; the last block may carry padding rows
-        if fwd_fn is None or bwd_fn is None:
-            from . import ops                 # CUDA kernels; raises on a machine without a GPU
-            fwd_fn = fwd_fn or (lambda g, X, out: ops.spmm_fwd(g, X, out=out))
-            bwd_fn = bwd_fn or (lambda g, dS, out: ops.spmm_bwd_x(g, dS, out=out))
-        self.fwd_fn, self.bwd_fn = fwd_fn, bwd_fn
+class GridSpMM:
+    def __init__(self, graph, D: int, world: int, rank: int, grid=None, *, exchange: str = "p2p", fwd_fn=None,
+                 bwd_fn=None, device=None, timeout_ms: int = 20000):
+        self.g, self.D, self.world, self.rank = graph, D, world, rank
+        self.P_r, self.P_c = parse_grid(grid, world, D)
+        self.pr, self.pc = grid_coords(rank, (self.P_r, self.P_c))
+        self.Dc = D // self.P_c
+        self.R, self.N = graph.R, graph.N
+        self.lo, self.hi, self.block = row_block(self.pr, self.P_r, self.N)
+        self.n_rows = self.hi - self.lo
+        if graph.n_rows != self.n_rows:
+            raise ValueError(f"graph holds {graph.n_rows} rows, grid position ({self.pr},{self.pc}) owns {self.n_rows}")
+        self.N_pad = self.block * self.P_r          # equal blocks for the collectives; the tail may be padding
+        self.group_ranks = [q * self.P_c + self.pc for q in range(self.P_r)]
+        self.peers = [q for q in range(self.P_r) if q != self.pr]          # group indices of the other ranks
+        self.injected = fwd_fn is not None or bwd_fn is not None
+        self.exchange = exchange if self.P_r > 1 else "none"
+        self.timeout_ms = timeout_ms
         dev = device if device is not None else graph.device
+        self.dev = dev
         f = dict(dtype=torch.float32, device=dev)
-        self.Xp_local = torch.zeros((panels, block, self.Dc), **f)
-        self.exchange, self.mc_ctas, self.nvls = exchange, mc_ctas, None
-        if exchange == "nvls":
-            # NVSwitch multicast exchange: both big buffers must be symmetric (same offset on every rank)
-            self.nvls = _NvlsBuffers((panels, self.N_pad, self.Dc), dev, dist.group.WORLD)
-            self.Xp_full, self.dXp_partial = self.nvls.full, self.nvls.partial
+        self.col_group = None
+        if self.P_r > 1 and (self.exchange == "nccl" or self.injected):
+            # every rank creates every column group (new_group is collective over the world)
+            for pc in range(self.P_c):
+                grp = dist.new_group([q * self.P_c + pc for q in range(self.P_r)])
+                if pc == self.pc:
+                    self.col_group = grp
+        if self.injected:
+            self.fwd_fn, self.bwd_fn = fwd_fn, bwd_fn
+            self.exchange = "nccl" if self.P_r > 1 else "none"
         else:
-            self.Xp_full = torch.empty((panels, self.N_pad, self.Dc), **f)
-            self.dXp_partial = torch.empty((panels, self.N_pad, self.Dc), **f)
-        self.dXp_local = torch.empty((panels, block, self.Dc), **f)
-        self.Sp = torch.empty((panels, self.R, self.n_rows, self.Dc), **f)
-        self.dSp = torch.empty((panels, self.R, self.n_rows, self.Dc), **f)
-        if self.N_pad != graph.N and graph.N > self.N_pad:
-            raise ValueError("block * world must cover all source nodes")
+            from . import _lib                    # CUDA library; raises on a machine without a GPU / nvcc
+            self._lib = _lib
+            self.lib = _lib.load()
+        self.epoch = 0
+        self.stage = None
+        if self.exchange == "p2p":
+            self._init_p2p()
+        else:
+            self.X_full = torch.zeros((self.N_pad, self.Dc), **f)
+            if self.exchange == "nccl":
+                self.dX_partial = torch.zeros((self.N_pad, self.Dc), **f)
+        self.S = torch.empty((self.R, self.n_rows, self.Dc), **f)
+        self.dS = torch.empty((self.R, self.n_rows, self.Dc), **f)
+        self.dX = torch.empty((max(self.block, 1), self.Dc), **f)[: self.block]
+        if not self.injected:
+            self.s_side = torch.cuda.Stream(device=dev, priority=-1)
+            self._lib.check(self.lib.iddgcn_spmm_prepare(graph.handle, self.Dc,
+                                                         torch.cuda.current_stream(dev).cuda_stream))
 
-    # -- layout helpers -----------------------------------------------------------------------------
+    # -- symmetric buffers of the fused exchange --------------------------------------------------------
+    def _init_p2p(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        dev, f32 = self.dev, torch.float32
+        nslot = max(self.P_r - 1, 1)
+        self.X_full = symm_mem.empty(self.N_pad, self.Dc, dtype=f32, device=dev)
+        self.stage = symm_mem.empty(nslot, self.block, self.Dc, dtype=f32, device=dev)
+        self.flags = symm_mem.empty(3 * SLOTS, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.X_full.zero_()
+        self.h_x = symm_mem.rendezvous(self.X_full, dist.group.WORLD)
+        self.h_stage = symm_mem.rendezvous(self.stage, dist.group.WORLD)
+        self.h_flags = symm_mem.rendezvous(self.flags, dist.group.WORLD)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier()                              # every rank's flags are zero before anyone signals
+        xp, sp, fp = self.h_x.buffer_ptrs, self.h_stage.buffer_ptrs, self.h_flags.buffer_ptrs
+        blk_bytes = self.block * self.Dc * 4
+        me = self.pr
+        self.peer_x_dst = []                        # where my X block goes in each peer's X_full
+        self.peer_stage_dst = []                    # my slot in each peer's stage buffer
+        for q in self.peers:
+            gr = self.group_ranks[q]
+            self.peer_x_dst.append(int(xp[gr]) + me * blk_bytes)
+            slot = me if me < q else me - 1
+            self.peer_stage_dst.append(int(sp[gr]) + slot * blk_bytes)
+
+        def slots(kind, remote):
+            arr = (C.c_void_p * len(self.peers))()
+            for i, q in enumerate(self.peers):
+                if remote:                          # my slot on peer q
+                    arr[i] = int(fp[self.group_ranks[q]]) + (kind * SLOTS + me) * 4
+                else:                               # peer q's slot here
+                    arr[i] = int(fp[self.rank]) + (kind * SLOTS + q) * 4
+            return arr
+
+        self.sig = {k: slots(k, True) for k in (K_DONE, K_AG, K_PART)}
+        self.wts = {k: slots(k, False) for k in (K_DONE, K_AG, K_PART)}
+
+    # -- views the caller fills / reads ---------------------------------------------------------------------
+    def x_local_view(self) -> torch.Tensor:
+        """This rank's block inside X_full: write the features here and the step needs no local copy."""
+        return self.X_full[self.lo:self.hi]
+
     def load_inputs(self, X_local: torch.Tensor, dS_local: torch.Tensor):
-        """Row-major rank-local inputs -> panel layout (done once per step's inputs, outside the exchange)."""
-        self.Xp_local[:, :self.n_rows].copy_(panelize(X_local, self.panels))
-        self.dSp.copy_(panelize(dS_local, self.panels))
+        """Rank-local inputs: X_local [n_rows, Dc], dS_local [R, n_rows, Dc] (this rank's column slice)."""
+        if X_local is not None:
+            self.x_local_view().copy_(X_local)
+        if dS_local is not None:
+            self.dS.copy_(dS_local)
 
     def outputs(self):
-        """(S_local [R,n_rows,D], dX_local [n_rows,D]) back in row-major layout."""
-        return unpanelize(self.Sp), unpanelize(self.dXp_local[:, :self.n_rows])
+        """(S_local [R, n_rows, Dc], dX_local [n_rows, Dc])."""
+        return self.S, self.dX[: self.n_rows]
 
-    # -- one exchange + compute step -------------------------------------------------------------------
-    def run_panels(self):
-        """One step: backward panels feed the reduce-scatter while the all-gather feeds the forward panels.
+    # -- primitives ---------------------------------------------------------------------------------------
+    def _st(self, stream=None):
+        return (stream or torch.cuda.current_stream(self.dev)).cuda_stream
 
-        Issue order on the compute stream is B0 F0 B1 F1 ...: backward panel c needs no exchange (dS is local), so its
-        kernel and the all-gather of panel c start together; its result goes straight into reduce-scatter c on the
-        second communicator while forward panel c consumes all-gather c."""
-        if self.nvls is not None:
-            return self._run_panels_nvls()
-        P = self.panels
-        gathers = [_all_gather(self.Xp_full[c], self.Xp_local[c], True, self.ag_group) for c in range(P)]
-        scatters = []
-        for c in range(P):
-            part = self.dXp_partial[c]
-            self.bwd_fn(self.g, self.dSp[c], part[: self.g.N])
-            if self.N_pad > self.g.N:
-                part[self.g.N:].zero_()
-            scatters.append(_reduce_scatter(self.dXp_local[c], part, self.rank, True, self.rs_group))
-            if gathers[c] is not None:
-                gathers[c].wait()
-            self.fwd_fn(self.g, self.Xp_full[c][: self.g.N], self.Sp[c])
-        for w in scatters:
-            if w is not None:
-                w.wait()
+    def _signal(self, kind, stream=None):
+        self._lib.check(self.lib.iddgcn_peer_signal(self.sig[kind], len(self.peers), self.epoch, self._st(stream)))
 
-    def _run_panels_nvls(self):
-        """Same step with the exchange done by our multimem kernels on two side streams.
+    def _wait(self, kind, value, stream=None):
+        self._lib.check(self.lib.iddgcn_peer_wait(self.wts[kind], len(self.peers), value, self.timeout_ms,
+                                                  self.timed_out.data_ptr(), self._st(stream)))
 
-        all-gather leg  : every rank stores its block of panel c once through the multicast address (the switch
-                          replicates it into every rank's Xp_full) -> barrier -> forward panel c may read it;
-        reduce-scatter  : after backward panel c on every rank (barrier), each rank loads ITS block of dXp_partial[c]
-                          through the multicast address with the in-switch sum.
-        The two legs load opposite link directions and run concurrently with the kernels."""
-        from ._lib import check, load
-        lib, nv, P = load(), self.nvls, self.panels
-        main = torch.cuda.current_stream(self.Xp_local.device)
-        blk = self.block * self.Dc                       # floats per (panel, rank) block
-        T_MS = 20000
-        for s_ in (nv.s_ag, nv.s_rs):
-            main.wait_stream(s_)
-        nv.h_full.barrier(channel=2, timeout_ms=T_MS)    # every rank is done with the previous step's buffers
-        nv.s_ag.wait_stream(main)
-        nv.s_rs.wait_stream(main)
-        ev_ag = []
-        with torch.cuda.stream(nv.s_ag):
-            for c in range(P):
-                off = (c * self.N_pad * self.Dc + self.rank * blk) * 4
-                check(lib.iddgcn_mc_store(nv.mc_full + off, self.Xp_local[c].data_ptr(), blk, self.mc_ctas,
-                                          nv.s_ag.cuda_stream))
-                nv.h_full.barrier(channel=0, timeout_ms=T_MS)
-                ev_ag.append(nv.s_ag.record_event())
-        ev_rs = []
-        for c in range(P):
-            part = self.dXp_partial[c]
-            self.bwd_fn(self.g, self.dSp[c], part[: self.g.N])
-            if self.N_pad > self.g.N:
-                part[self.g.N:].zero_()
-            ev_b = main.record_event()
-            with torch.cuda.stream(nv.s_rs):
-                nv.s_rs.wait_event(ev_b)
-                nv.h_part.barrier(channel=0, timeout_ms=T_MS)    # every rank's partial panel c is complete
-                off = (c * self.N_pad * self.Dc + self.rank * blk) * 4
-                check(lib.iddgcn_mc_reduce_load(nv.mc_part + off, self.dXp_local[c].data_ptr(), blk, self.mc_ctas,
-                                                nv.s_rs.cuda_stream))
-                ev_rs.append(nv.s_rs.record_event())
-            main.wait_event(ev_ag[c])
-            self.fwd_fn(self.g, self.Xp_full[c][: self.g.N], self.Sp[c])
-        for e in ev_rs:
-            main.wait_event(e)
+    def _fwd(self, lo=0, hi=None, stream=None):
+        """S rows [lo, hi) of the flattened [R·n_rows] output."""
+        total = self.R * self.n_rows
+        hi = total if hi is None else hi
+        if hi <= lo:
+            return
+        out = self.S.data_ptr() + lo * self.Dc * 4
+        self._lib.check(self.lib.iddgcn_spmm_fwd_rows(self.g.handle, self.X_full.data_ptr(), self.Dc, None, 0, out, lo,
+                                                      hi, self._st(stream)))
 
-    def step(self, X_local, dS_local, S_out=None):
-        """bench.py's step: inputs are already resident in panel layout after the first call."""
-        if not getattr(self, "_loaded", False):
+    def _bwd_rows(self, dst_ptr, node_lo, node_hi, addends=(), stream=None):
+        if node_hi <= node_lo:
+            return
+        arr = (C.c_void_p * max(len(addends), 1))(*addends) if addends else None
+        self._lib.check(self.lib.iddgcn_spmm_bwd_x_rows(self.g.handle, self.dS.data_ptr(), self.Dc, None, 0, dst_ptr,
+                                                        node_lo, node_hi, arr, len(addends), self._st(stream)))
+
+    def _push_partials(self, stream=None):
+        """Backward over the node blocks owned by peers, written straight into their stage buffers (NVLink)."""
+        for i, q in enumerate(self.peers):
+            qlo, qhi, _ = row_block(q, self.P_r, self.N)
+            self._bwd_rows(self.peer_stage_dst[i], qlo, qhi, stream=stream)
+
+    def _own_partial(self, a=0, b=None, stream=None):
+        """Backward over (a chunk [a, b) of) this rank's own node block, folding in the staged peer partials."""
+        b = self.n_rows if b is None else b
+        off = a * self.Dc * 4
+        adds = [self.stage.data_ptr() + (s * self.block * self.Dc) * 4 + off for s in range(len(self.peers))] \
+            if self.exchange == "p2p" else []
+        self._bwd_rows(self.dX.data_ptr() + off, self.lo + a, self.lo + b, adds, stream=stream)
+
+    def _push_x(self, stream):
+        """Copy engines: this rank's X block into every peer's X_full."""
+        src = self.X_full.data_ptr() + self.lo * self.Dc * 4
+        nbytes = self.n_rows * self.Dc * 4
+        for dst in self.peer_x_dst:
+            self._lib.check(self.lib.iddgcn_copy_async(dst, src, nbytes, stream.cuda_stream))
+
+    # -- one exchange + compute step ------------------------------------------------------------------------
+    def step(self, X_local=None, dS_local=None):
+        """Inputs given here are loaded first (outside of what bench.py times they are already resident)."""
+        if X_local is not None or dS_local is not None:
             self.load_inputs(X_local, dS_local)
-            self._loaded = True
-        self.run_panels()
+        if self.injected:
+            return self._step_injected()
+        if self.exchange == "p2p":
+            return self._step_p2p()
+        if self.exchange == "nccl":
+            return self._step_nccl()
+        self._fwd()                                    # P_r == 1: nothing to exchange
+        self._own_partial()
 
-    # -- measurement helpers used by bench.py ---------------------------------------------------------
-    def kernel_times(self, X_local, dS_local, S_out, iters=5):
-        """Per-rank compute-only times (no collectives): all panels fwd, all panels bwd."""
+    def _step_p2p(self):
+        main, side = torch.cuda.current_stream(self.dev), self.s_side
+        self.epoch += 1
+        e = self.epoch
+        self._wait(K_DONE, e - 1)                      # peers are done reading what I pushed in the previous step
+        ev0 = main.record_event()
+        side.wait_event(ev0)
+        self._push_x(side)                             # all-gather leg on the copy engines ...
+        self._signal(K_AG, side)
+        self._push_partials()                          # ... while the backward kernel streams partials to the peers
+        self._signal(K_PART)
+        self._wait(K_AG, e)                            # every peer's X block has landed here
+        self._fwd()
+        self._wait(K_PART, e)                          # every peer's partials for my nodes have landed
+        self._own_partial()
+        self._signal(K_DONE)
+        main.wait_stream(side)
+
+    def _step_nccl(self):
+        grp = self.col_group
+        ag = dist.all_gather_into_tensor(self.X_full, self.X_full[self.pr * self.block:(self.pr + 1) * self.block],
+                                         group=grp, async_op=True)
+        self._bwd_rows(self.dX_partial.data_ptr(), 0, self.N)
+        rs = _reduce_scatter(self.dX, self.dX_partial, self.pr, grp)
+        ag.wait()
+        self._fwd()
+        if rs is not None:
+            rs.wait()
+
+    def _step_injected(self):
+        """CPU host-logic path of the gloo tests: same partition arithmetic, compute from the injected functions."""
+        if self.P_r > 1:
+            mine = self.X_full[self.pr * self.block:(self.pr + 1) * self.block].clone()
+            dist.all_gather_into_tensor(self.X_full, mine, group=self.col_group)
+        self.fwd_fn(self.g, self.X_full[: self.N], self.S)
+        part = torch.zeros((self.N_pad, self.Dc), dtype=torch.float32)
+        self.bwd_fn(self.g, self.dS, part[: self.N])
+        if self.P_r > 1:
+            _reduce_scatter(self.dX, part, self.pr, self.col_group)
+        else:
+            self.dX.copy_(part[: self.block])
+
+    def check_timeouts(self):
+        if self.exchange == "p2p" and int(self.timed_out.item()) != 0:
+            raise RuntimeError("a peer flag wait timed out: the exchange results are invalid")
+
+    # -- measurement helpers used by bench.py -------------------------------------------------------------
+    def kernel_times(self, iters=5):
+        """Per-rank compute-only times (no exchange, no waits): forward over the row block; backward over all N nodes
+        (peer blocks + own block) written locally."""
         out = {"fwd": [], "bwd": []}
+        scratch = torch.empty((self.N, self.Dc), dtype=torch.float32, device=self.dev)
         for _ in range(iters):
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
-            for p in range(self.panels):
-                self.fwd_fn(self.g, self.Xp_full[p][: self.g.N], self.Sp[p])
+            self._fwd()
             b.record()
-            for p in range(self.panels):
-                self.bwd_fn(self.g, self.dSp[p], self.dXp_partial[p][: self.g.N])
+            self._bwd_rows(scratch.data_ptr(), 0, self.N)
             c.record()
-            torch.cuda.synchronize()
+            torch.cuda.synchronize(self.dev)
             out["fwd"].append(a.elapsed_time(b))
             out["bwd"].append(b.elapsed_time(c))
+        del scratch
         return out
 
-    def comm_times(self, iters=5):
-        """Per-rank collective-only times: all panels all-gather, all panels reduce-scatter."""
-        out = {"all_gather": [], "reduce_scatter": []}
+    def exchange_times(self, iters=5):
+        """Per-rank exchange-only times: the all-gather push alone and a plain peer copy of the partial volume."""
+        if self.exchange != "p2p":
+            return None
+        out = {"all_gather_push": [], "partial_push": []}
+        nbytes = self.n_rows * self.Dc * 4
         for _ in range(iters):
-            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             dist.barrier()
+            torch.cuda.synchronize(self.dev)
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            main = torch.cuda.current_stream(self.dev)
             a.record()
-            for p in range(self.panels):
-                _all_gather(self.Xp_full[p], self.Xp_local[p], False, self.ag_group)
+            self._push_x(main)
             b.record()
-            for p in range(self.panels):
-                _reduce_scatter(self.dXp_local[p], self.dXp_partial[p], self.rank, False, self.rs_group)
+            for i, q in enumerate(self.peers):          # same bytes as the fused partial stores, as a DMA
+                qlo, qhi, _ = row_block(q, self.P_r, self.N)
+                self._lib.check(self.lib.iddgcn_copy_async(self.peer_stage_dst[i], self.dX.data_ptr(),
+                                                           min(nbytes, (qhi - qlo) * self.Dc * 4), main.cuda_stream))
             c.record()
-            torch.cuda.synchronize()
-            out["all_gather"].append(a.elapsed_time(b))
-            out["reduce_scatter"].append(b.elapsed_time(c))
+            torch.cuda.synchronize(self.dev)
+            out["all_gather_push"].append(a.elapsed_time(b))
+            out["partial_push"].append(b.elapsed_time(c))
+        dist.barrier()
         return out
 
-    def e2e(self, args, nnz_global):
-        """Same step with HOST buffers: pinned X/dS blocks up, S/dX blocks down, every step; max over ranks."""
-        Xh = self.Xp_local.cpu().pin_memory()
-        dSh = self.dSp.cpu().pin_memory()
-        Sh = torch.empty(self.Sp.shape).pin_memory()
-        dXh = torch.empty(self.dXp_local.shape).pin_memory()
-        k = max(3, min(args.steps, 5))
+    # -- end to end with host buffers -----------------------------------------------------------------------
+    def step_host(self, Xh, dSh, Sh, dXh, chunks: int = 4):
+        """One step with pinned HOST blocks in and out: X_local/dS_local up, S_local/dX_local down.
 
-        def one():
-            self.Xp_local.copy_(Xh, non_blocking=True)
-            self.dSp.copy_(dSh, non_blocking=True)
-            self.run_panels()
-            Sh.copy_(self.Sp, non_blocking=True)
-            dXh.copy_(self.dXp_local, non_blocking=True)
+        Three streams: uploads, compute, downloads.  X (the smaller input) goes up first so that the all-gather and
+        the forward start early; S flows back in row chunks while dS is still on its way up; the backward's own block is
+        cut into node chunks so that dX starts flowing back before the kernel has finished."""
+        lib, chk = self.lib, self._lib.check
+        main = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "s_in"):
+            self.s_in = torch.cuda.Stream(device=self.dev)
+            self.s_out = torch.cuda.Stream(device=self.dev)
+        s_in, s_out = self.s_in, self.s_out
+        p2p = self.exchange == "p2p"
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        if p2p:
+            self.epoch += 1
+            e = self.epoch
+            self._wait(K_DONE, e - 1, s_in)            # peers no longer read my X block of the previous step
+        xv = self.x_local_view()
+        chk(lib.iddgcn_copy_async(xv.data_ptr(), Xh.data_ptr(), xv.numel() * 4, s_in.cuda_stream))
+        if p2p:
+            self._push_x(s_in)
+            self._signal(K_AG, s_in)
+        ev_x = s_in.record_event()
+        chk(lib.iddgcn_copy_async(self.dS.data_ptr(), dSh.data_ptr(), self.dS.numel() * 4, s_in.cuda_stream))
+        ev_ds = s_in.record_event()
+        main.wait_event(ev_x)
+        if p2p:
+            self._wait(K_AG, e)
+        elif self.exchange == "nccl":
+            dist.all_gather_into_tensor(self.X_full, self.X_full[self.pr * self.block:(self.pr + 1) * self.block],
+                                        group=self.col_group)
+        total = self.R * self.n_rows
+        row_bytes = self.Dc * 4
+        for q in range(chunks):
+            lo, hi = total * q // chunks, total * (q + 1) // chunks
+            self._fwd(lo, hi)
+            s_out.wait_event(main.record_event())
+            chk(lib.iddgcn_copy_async(Sh.data_ptr() + lo * row_bytes, self.S.data_ptr() + lo * row_bytes,
+                                      (hi - lo) * row_bytes, s_out.cuda_stream))
+        main.wait_event(ev_ds)
+        if p2p:
+            self._push_partials()
+            self._signal(K_PART)
+            self._wait(K_PART, e)
+        elif self.exchange == "nccl":
+            self._bwd_rows(self.dX_partial.data_ptr(), 0, self.N)
+            dist.reduce_scatter_tensor(self.dX, self.dX_partial, group=self.col_group)
+        for q in range(chunks):
+            a, b = self.n_rows * q // chunks, self.n_rows * (q + 1) // chunks
+            if self.exchange != "nccl":
+                self._own_partial(a, b)
+            s_out.wait_event(main.record_event())
+            chk(lib.iddgcn_copy_async(dXh.data_ptr() + a * row_bytes, self.dX.data_ptr() + a * row_bytes,
+                                      (b - a) * row_bytes, s_out.cuda_stream))
+        if p2p:
+            self._signal(K_DONE)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
 
-        one()
-        torch.cuda.synchronize()
+    def e2e(self, steps, nnz_global):
+        """bench.py's e2e leg at N > 1: every rank moves its own blocks over its own PCIe link; max over ranks."""
+        Xh = self.x_local_view().cpu().pin_memory()
+        dSh = self.dS.cpu().pin_memory()
+        Sh = torch.empty(self.S.shape).pin_memory()
+        dXh = torch.empty((self.n_rows, self.Dc)).pin_memory()
+        k = max(3, min(steps, 5))
+        # raw PCIe rate of this rank with every rank copying at once (what bounds the step)
+        dist.barrier()
+        torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        self.dS.copy_(dSh, non_blocking=True)
+        torch.cuda.synchronize(self.dev)
+        h2d = dSh.numel() * 4 / (time.perf_counter() - t0) / 1e9
+        for _ in range(2):
+            self.step_host(Xh, dSh, Sh, dXh)
+        torch.cuda.synchronize(self.dev)
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(k):
-            one()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / k], dtype=torch.float64, device=self.Xp_local.device)
+            self.step_host(Xh, dSh, Sh, dXh)
+        torch.cuda.synchronize(self.dev)
+        dt = torch.tensor([(time.perf_counter() - t0) / k, h2d, -h2d], dtype=torch.float64, device=self.dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt.item())
-        return {"value": nnz_global / dt, "unit": "edges/s",
-                "h2d_bytes_per_step": (Xh.numel() + dSh.numel()) * 4 * self.world,
-                "d2h_bytes_per_step": (Sh.numel() + dXh.numel()) * 4 * self.world, "ms_per_step": dt * 1e3, "steps": k,
-                "api": "PartitionedSpMM.run_panels with pinned host blocks in/out on every rank"}
+        step_s, h2d_max, h2d_min = float(dt[0]), float(dt[1]), -float(dt[2])
+        up = (Xh.numel() + dSh.numel()) * 4
+        down = (Sh.numel() + dXh.numel()) * 4
+        res = {"value": nnz_global / step_s, "unit": "edges/s", "h2d_bytes_per_step": up * self.world,
+               "d2h_bytes_per_step": down * self.world, "ms_per_step": step_s * 1e3, "steps": k,
+               "per_rank_pcie_GBps": {"up+down_in_step": (up + down) / step_s / 1e9,
+                                      "h2d_alone_all_ranks_at_once_min": h2d_min,
+                                      "h2d_alone_all_ranks_at_once_max": h2d_max},
+               "api": "GridSpMM.step_host: pinned host blocks in/out on every rank (3-stream pipeline)"}
+        del Xh, dSh, Sh, dXh
+        return res

@@ -50,12 +50,38 @@ def spmm_bwd_x(graph: Graph, dS: torch.Tensor, vals=None, mode: int = VALS_ONES,
     return dX
 
 
-def spmm_bwd_vals(graph: Graph, dS: torch.Tensor, X: torch.Tensor, vals=None, mode: int = VALS_ONES) -> torch.Tensor:
+def spmm_fwd_rows(graph: Graph, X: torch.Tensor, S: torch.Tensor, row_begin: int, row_end: int, vals=None,
+                  mode: int = VALS_ONES) -> None:
+    """Rows [row_begin, row_end) of the flattened (R·n_rows, D) output only (pipelined callers); S is the FULL buffer."""
+    X = _f32c(X, "X")
+    D = X.shape[1]
+    Sf = S.view(-1, D)
+    with torch.cuda.device(X.device):
+        check(load().iddgcn_spmm_fwd_rows(graph.handle, ptr(X), D, ptr(vals), mode, Sf[row_begin:].data_ptr(),
+                                          row_begin, row_end, _stream(X)))
+
+
+def spmm_bwd_x_rows(graph: Graph, dS: torch.Tensor, dX_rows: torch.Tensor, node_begin: int, node_end: int,
+                    addends=(), vals=None, mode: int = VALS_ONES) -> None:
+    """dX rows of source nodes [node_begin, node_end) into dX_rows (first row = node_begin; may be peer memory), plus
+    the addends (tensors or raw addresses, each at the first row of the range) summed in the kernel epilogue."""
+    dS = _f32c(dS, "dS")
+    D = dS.shape[-1]
+    addrs = [a if isinstance(a, int) else a.data_ptr() for a in addends]
+    arr = (C.c_void_p * max(len(addrs), 1))(*addrs) if addrs else None
+    dst = dX_rows if isinstance(dX_rows, int) else dX_rows.data_ptr()
+    with torch.cuda.device(dS.device):
+        check(load().iddgcn_spmm_bwd_x_rows(graph.handle, ptr(dS), D, ptr(vals), mode, dst, node_begin, node_end, arr,
+                                            len(addrs), _stream(dS)))
+
+
+def spmm_bwd_vals(graph: Graph, dS: torch.Tensor, X: torch.Tensor, vals=None, mode: int = VALS_ONES,
+                  out=None) -> torch.Tensor:
     """∂L/∂vals[e] = <dS[row_e], X[col_e]> (·σ'(v) in SIGMOID mode) — SDDMM on the CSR pattern."""
     dS = _f32c(dS, "dS")
     X = _f32c(X, "X")
     D = X.shape[1]
-    dv = torch.empty(graph.nnz, dtype=torch.float32, device=X.device)
+    dv = out if out is not None else torch.empty(graph.nnz, dtype=torch.float32, device=X.device)
     with torch.cuda.device(X.device):
         check(load().iddgcn_spmm_bwd_vals(graph.handle, ptr(dS), ptr(X), D, ptr(vals), mode, ptr(dv), _stream(X)))
     return dv

@@ -131,6 +131,26 @@ int iddgcn_spmm_bwd_vals(const iddgcn_graph_t* g, const float* dS, const float* 
 int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_mode,
                            float* out_per_rel, void* stream);
 
+/* Row-range flavours (same kernels, same reference lines: IDDGCN.py:70 and its TF gradient).
+ * A caller that pipelines a step (chunked host copies, or the grid-partitioned multi-GPU step of dist.py) computes
+ * only part of the output rows per call:
+ *   iddgcn_spmm_fwd_rows   : S rows [row_begin,row_end) of the flattened [R*n_rows, D] output; S_rows points at the
+ *                            FIRST row of the range.
+ *   iddgcn_spmm_bwd_x_rows : dX rows of source nodes [node_begin,node_end); dX_rows points at the first of them and
+ *                            may be memory of a PEER GPU mapped into this process (NVLink peer stores: the partial
+ *                            rows land in the owner's stage buffer as they are produced — a fused reduce-scatter).
+ *                            addends[0..n_addends) (<= 8, host array of device pointers, each at the first row of the
+ *                            range) are added to the gathered sum in the epilogue in the order given:
+ *                            dX_rows[k] = Σ_r A_rᵀ dS_r [k] + Σ_j addends[j][k]   (how the owner folds the partials its
+ *                            peers pushed; n_addends=1 with addends[0]==dX_rows is the classic "accumulate").
+ *   iddgcn_spmm_prepare    : size the hub-row workspace for feature width D now (needed before a stream capture). */
+int iddgcn_spmm_fwd_rows(const iddgcn_graph_t* g, const float* X, int64_t D, const float* vals, int vals_mode,
+                         float* S_rows, int64_t row_begin, int64_t row_end, void* stream);
+int iddgcn_spmm_bwd_x_rows(const iddgcn_graph_t* g, const float* dS, int64_t D, const float* vals, int vals_mode,
+                           float* dX_rows, int64_t node_begin, int64_t node_end,
+                           const float* const* addends, int n_addends, void* stream);
+int iddgcn_spmm_prepare(const iddgcn_graph_t* g, int64_t D, void* stream);
+
 /* End-to-end variant with HOST buffers (pinned or pageable): uploads X and dS,
  * runs fwd + bwd_x, downloads S and dX; copies are chunked and overlapped with
  * the kernels on internal streams.  Blocking.  Any of S_host/dX_host may be
@@ -330,6 +350,26 @@ int iddgcn_structure_grad(const iddgcn_graph_t* g, const float* vals, int vals_m
  * ------------------------------------------------------------------------ */
 int iddgcn_mc_store(void* mc_dst, const float* src, int64_t n, int ctas, void* stream);
 int iddgcn_mc_reduce_load(const void* mc_src, float* dst, int64_t n, int ctas, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Plumbing of the fused peer-memory exchange of the grid-partitioned SpMM (dist.py; no reference counterpart, see
+ * above).  Ranks order their steps with 32-bit epoch flags in symmetric memory instead of host barriers:
+ *   iddgcn_peer_signal : once everything enqueued before it on `stream` is done, store `value` (release, system scope)
+ *                        into remote_slots[0..n) — one slot on each peer (peer-mapped addresses).
+ *   iddgcn_peer_wait   : hold `stream` until every local_slots[i] has reached `value` (wrap-safe compare); after
+ *                        timeout_ms (<=0: 20000) it gives up and sets *timed_out_dev (device int, may be NULL) to 1.
+ *   iddgcn_copy_async / iddgcn_copy2d_async : cudaMemcpy(2D)Async with cudaMemcpyDefault — copy-engine transfers
+ *                        between any of host / device / peer memory (the all-gather push and the host pipelines).
+ *   iddgcn_peer_push   : the same push done by `ctas` thread blocks with 16-byte stores (A/B alternative to the DMA).
+ * n <= 8 peers.
+ * ------------------------------------------------------------------------ */
+int iddgcn_peer_signal(void* const* remote_slots, int n, uint32_t value, void* stream);
+int iddgcn_peer_wait(void* const* local_slots, int n, uint32_t value, int timeout_ms, int* timed_out_dev,
+                     void* stream);
+int iddgcn_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
+int iddgcn_copy2d_async(void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width_bytes,
+                        int64_t rows, void* stream);
+int iddgcn_peer_push(float* dst_peer, const float* src, int64_t n, int ctas, void* stream);
 
 #ifdef __cplusplus
 }

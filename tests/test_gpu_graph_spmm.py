@@ -308,3 +308,65 @@ def test_hub_rows_take_the_split_pass(D, mode, kernels, monkeypatch):
     dv = ops.spmm_bwd_vals(g, dSd, Xd, vd, mode).cpu().numpy()
     assert rel_err(dv, dv_ref, scale=np.abs(dS).max() * np.abs(X).max() * np.sqrt(D)) < TOL
     assert torch.equal(ops.spmm_fwd(g, Xd, vd, mode), torch.from_numpy(S).cuda())     # still bit-reproducible
+
+
+@pytest.mark.parametrize("D", [16, 32, 128])
+def test_row_ranges_addends_and_hub_rows_v2(D, monkeypatch):
+    """The range entry points the pipelined / partitioned callers use (iddgcn_spmm_fwd_rows, iddgcn_spmm_bwd_x_rows with
+    epilogue addends) on a graph with hub rows AND hub columns, v2 kernels forced: chunked calls reproduce the
+    one-shot result bit for bit, addends are summed in order, and the v2 SDDMM skips / fills hub rows correctly."""
+    monkeypatch.setenv("IDDGCN_SPMM_V1", "0")
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R = 6000, 2
+    tri = random_triples(N, R, 50000, seed=D, heavy_row=11)
+    hub_col = tri[:9000].copy()
+    hub_col[:, 2] = 17                              # > 1024 in-edges of node 17: a hub on the backward side too
+    empties = tri[(tri[:, 0] % 7) != 3]             # whole runs of empty rows between non-empty ones
+    tri = np.concatenate([empties, hub_col], 0)
+    adj = O.get_adj_mats(tri, N, R)
+    g = Graph(tri, N, R)
+    rng = np.random.default_rng(D)
+    X = rng.random((N, D)).astype(np.float32)
+    dS = rng.standard_normal((R, N, D)).astype(np.float32)
+    Xd, dSd = torch.from_numpy(X).cuda(), torch.from_numpy(dS).cuda()
+    S_full = ops.spmm_fwd(g, Xd)
+    assert rel_err(S_full.cpu().numpy(), O.spmm_fwd(adj, X.astype(np.float64))) < TOL
+    S_chunks = torch.full_like(S_full, -7.0)
+    total = R * N
+    for lo, hi in [(0, 1), (1, 4001), (4001, 4001), (4001, total)]:
+        ops.spmm_fwd_rows(g, Xd, S_chunks, lo, hi)
+    assert torch.equal(S_chunks, S_full)
+    dX_full = ops.spmm_bwd_x(g, dSd)
+    assert rel_err(dX_full.cpu().numpy(), O.spmm_bwd_x(adj, dS.astype(np.float64))) < TOL
+    a1 = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).cuda()
+    a2 = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).cuda()
+    out = torch.full((N, D), -7.0, device="cuda")
+    for lo, hi in [(0, 18), (18, 3000), (3000, N)]:
+        ops.spmm_bwd_x_rows(g, dSd, out[lo:], lo, hi, addends=[a1[lo:], a2[lo:]])
+    assert torch.equal(out, (dX_full + a1) + a2)
+    plain = torch.empty((N, D), device="cuda")
+    ops.spmm_bwd_x_rows(g, dSd, plain, 0, N)
+    assert torch.equal(plain, dX_full)
+    # SDDMM with hub rows, three modes (ones / explicit share the kernel)
+    for mode in (1, 2):
+        raw, eff = _vals_for(adj, mode, seed=5)
+        vd = torch.from_numpy(raw).cuda()
+        dv_ref = np.concatenate(O.spmm_bwd_vals(adj, dS.astype(np.float64), X.astype(np.float64)))
+        if mode == 2:
+            s_ = np.concatenate(eff)
+            dv_ref = dv_ref * s_ * (1 - s_)
+        dv = ops.spmm_bwd_vals(g, dSd, Xd, vd, mode).cpu().numpy()
+        assert rel_err(dv, dv_ref, scale=np.abs(dS).max() * np.abs(X).max() * np.sqrt(D)) < TOL
+
+
+def test_empty_row_block_graph():
+    """A trailing rank of a partition may own no rows (N not divisible by the number of blocks): the handle builds,
+    reports nnz = 0, and the backward over its (empty) block writes zeros."""
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    tri = random_triples(50, 2, 400, seed=1)
+    g = Graph(tri, 50, 2, row_block=(50, 50))
+    assert g.n_rows == 0 and g.nnz == 0
+    dX = ops.spmm_bwd_x(g, torch.zeros((2, 0, 8), device="cuda"))
+    assert dX.shape == (50, 8) and float(dX.abs().max()) == 0.0

@@ -109,19 +109,30 @@ def test_bench_algorithmic_bytes_match_survey():
 
 
 def test_bench_cpu_inputs_are_a_valid_graph():
+    """The CPU arm's structure is the CSR/CSC of the SAME raw edge list the GPU arm builds its graph from
+    (bench.raw_edges), and the two feature generators (NumPy for the CPU arm / the parity check, torch for the device)
+    agree bit for bit."""
+    import torch
     import bench
     from oracle import iddgcn_oracle as O
     wl = dict(bench.WORKLOADS["small"]); wl["name"] = "small"; wl["N"] = 2000; wl["per_rel"] = 15000
-    struct, N, n_rows, nnz, X, dS, sample = bench.cpu_sample_inputs(wl)
-    rng = np.random.default_rng(0)
+    struct, N, nnz, X, dS, sample = bench.cpu_sample_inputs(wl)
     tri = []
     for r in range(wl["R"]):
-        h = rng.integers(0, N, wl["per_rel"]); t = rng.integers(0, N, wl["per_rel"])
+        h, t = bench.raw_edges(N, wl["per_rel"], r)
         tri.append(np.stack([h, np.full_like(h, r), t], 1))
     ref = O.csr_csc_from_adj(O.get_adj_mats(np.concatenate(tri), N, wl["R"]), N)
     for k in struct:
         assert np.array_equal(struct[k], ref[k]), k
     assert nnz == ref["nnz"]
+    ids = np.array([0, 1, 77, N - 1, 2 * N - 1], np.int64)
+    for kind, full in (("X", X), ("dS", dS)):
+        a = bench.gen_rows_np(kind, ids, 32, 64, wl["D"])
+        b = bench.gen_rows_torch(torch, kind, torch.from_numpy(ids), 32, 64, wl["D"]).numpy()
+        assert np.array_equal(a, b)
+        ok = ids < full.shape[0]
+        assert np.array_equal(full[ids[ok], 32:96], a[ok])
+    assert 0.45 < X.mean() < 0.55 and abs(dS.mean()) < 0.05 and 0.9 < dS.std() < 1.1
 
 
 def test_product_fold_pipeline_matches_oracle_and_shipped_files(golden_dir):

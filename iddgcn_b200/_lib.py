@@ -48,6 +48,9 @@ _SIGNATURES = {
     "iddgcn_spmm_fwd_bwd_host": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp]),
     "iddgcn_spmm_fwd_dl": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "iddgcn_spmm_bwd_x_dl": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, vp]),
+    "iddgcn_layer_fwd_dl": (C.c_int, [vp] * 9),
+    "iddgcn_layer_bwd_dl": (C.c_int, [vp] * 10 + [C.c_int] + [vp] * 4),
+    "iddgcn_model_forward_dl": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
     "iddgcn_plan_create": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int, C.c_int64, C.c_int, vp, C.POINTER(vp)]),
     "iddgcn_plan_destroy": (C.c_int, [vp]),
     "iddgcn_relation_transform": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_int64, vp, vp]),
@@ -66,6 +69,7 @@ _SIGNATURES = {
     "iddgcn_model_param_layout": (C.c_int, [vp, c_i64p, c_i64p]),
     "iddgcn_model_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 4),
     "iddgcn_model_release_plan": (C.c_int, [vp, vp]),
+    "iddgcn_model_release_graph": (C.c_int, [vp, vp]),
     "iddgcn_model_forward": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
     "iddgcn_model_train_step": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                           C.c_int, vp, vp, vp]),

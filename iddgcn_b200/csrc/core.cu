@@ -92,6 +92,11 @@ void pool_trim() {
   pool_trim_locked();
 }
 
+uint64_t next_handle_uid() {
+  static std::atomic<uint64_t> next{1};
+  return next.fetch_add(1, std::memory_order_relaxed);
+}
+
 static thread_local char t_error[512] = "";
 std::atomic<int64_t> g_launches{0};
 

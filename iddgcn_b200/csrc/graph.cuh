@@ -5,7 +5,12 @@
 
 constexpr int HEAVY_EDGES = 1024;
 
+namespace iddgcn {
+uint64_t next_handle_uid();   // core.cu: monotonically increasing ids (a recycled heap address never repeats an id)
+}
+
 struct iddgcn_graph {
+  uint64_t uid = iddgcn::next_handle_uid();
   int device = 0;
   int64_t N = 0;        // source nodes (columns)
   int64_t n_rows = 0;   // destination rows held here (row_hi - row_lo)
@@ -35,7 +40,8 @@ struct iddgcn_graph {
     int32_t* segptr = nullptr;    // [H+1] first segment of each hub row
   };
   HeavyList heavy_fwd, heavy_bwd;
-  mutable float* heavy_ws = nullptr;   // [total_segs, D] partial sums (grown on demand, never inside a stream capture)
+  mutable float* heavy_ws = nullptr;   // [total_segs, D] partial sums: iddgcn_spmm_prepare, or grown on first use (pooled;
+                                       // refused while the stream is being captured)
   mutable size_t heavy_ws_elems = 0;
   float* rel_sums_scratch = nullptr;
   // lazily created by iddgcn_spmm_fwd_bwd_host and kept for the next call (mutable cache)
@@ -47,6 +53,7 @@ struct iddgcn_graph {
 
 // Triples of one model call, plus the orderings that make every gather-backward a segment sum.
 struct iddgcn_plan {
+  uint64_t uid = iddgcn::next_handle_uid();
   int device = 0;
   int64_t T = 0;
   int64_t N = 0;

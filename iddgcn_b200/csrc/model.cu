@@ -9,6 +9,7 @@
 #include <unordered_map>
 #include <vector>
 #include "dense.cuh"
+#include "dlpack.cuh"
 #include "graph.cuh"
 #include "triple.cuh"
 
@@ -17,6 +18,7 @@ int spmm_fwd_range(const iddgcn_graph* g, const float* X, int64_t D, const float
                    int64_t row_begin, int64_t row_end, cudaStream_t st);
 int spmm_bwd_x_range(const iddgcn_graph* g, const float* dS, int64_t D, const float* vals, int mode, float* dX,
                      int accumulate, int64_t row_begin, int64_t row_end, cudaStream_t st);
+int spmm_prepare(const iddgcn_graph* g, int64_t D, cudaStream_t st);
 }  // namespace iddgcn
 
 using namespace iddgcn;
@@ -62,10 +64,15 @@ struct iddgcn_model {
   // positives and negatives of a train step run as ONE batch of triples: (pos, neg) -> concatenated plan
   struct Merged { const iddgcn_plan* pos; const iddgcn_plan* neg; iddgcn_plan* both; };
   std::vector<Merged> merged;
-  // captured training step
+  // captured training step.  The CUDA graph bakes in raw device pointers (workspaces of this handle, the graph's
+  // CSR arrays and hub workspace, the plans' index arrays), so it is keyed on the handles' UNIQUE IDS (never on heap
+  // addresses, which are recycled) and on ws_gen, which every (re)allocation of a captured workspace bumps.
   cudaGraphExec_t graph_exec = nullptr;
-  const void* graph_key[3] = {nullptr, nullptr, nullptr};
+  uint64_t graph_uid[3] = {0, 0, 0};
+  uint64_t graph_gen = 0;
+  const void* graph_heavy_ws = nullptr;
   float graph_hyper[4] = {0, 0, 0, 0};
+  uint64_t ws_gen = 1;
   cudaStream_t own_stream = nullptr;
 
   float* P(int64_t off) const { return params + off; }
@@ -105,10 +112,20 @@ static void model_free(iddgcn_model* m) {
   delete m;
 }
 
+constexpr size_t MAX_TRIPLE_WS = 8;   // distinct triple counts kept alive per model
+
 static int ensure_triple_ws(iddgcn_model* m, const iddgcn_plan* p, TripleWS** out) {
+  if (m->ws.find(p->T) == m->ws.end() && m->ws.size() >= MAX_TRIPLE_WS) {
+    // a stream of differently sized plans would otherwise grow the map without bound: drop every other size
+    IDD_CUDA(cudaDeviceSynchronize());
+    for (auto& kv : m->ws) kv.second.release();
+    m->ws.clear();
+    ++m->ws_gen;
+  }
   TripleWS& w = m->ws[p->T];
   if (w.T != p->T || w.HT.empty()) {
     w.release();
+    ++m->ws_gen;
     const size_t td = (size_t)(p->T ? p->T : 1) * m->D;
     const size_t tr = (size_t)(p->T ? p->T : 1) * m->R;
     for (int l = 0; l <= m->L; ++l) {
@@ -133,11 +150,11 @@ static int ensure_triple_ws(iddgcn_model* m, const iddgcn_plan* p, TripleWS** ou
   size_t g3 = gemm_tn_workspace_elems(m->D, m->D, m->N, m->R);
   if (g2 > gw) gw = g2;
   if (g3 > gw) gw = g3;
-  if (gw > m->gemm_ws.n) IDD_CUDA(m->gemm_ws.ensure(gw));
+  if (gw > m->gemm_ws.n) { IDD_CUDA(m->gemm_ws.ensure(gw)); ++m->ws_gen; }
   size_t sw = colsum_scratch_elems(p->T, m->R);
   size_t s2 = distmult_scratch_elems(p, m->D);
   if (s2 > sw) sw = s2;
-  if (sw > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(sw));
+  if (sw > m->small_ws.n) { IDD_CUDA(m->small_ws.ensure(sw)); ++m->ws_gen; }
   *out = &w;
   return IDDGCN_OK;
 }
@@ -280,10 +297,12 @@ static int prepare_train(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_pl
   }
   IDD_TRY(ensure_triple_ws(m, b, w));
   const size_t Tt = (size_t)b->T;
-  if (Tt > m->y_all.n) IDD_CUDA(m->y_all.ensure(Tt));
-  if (Tt > m->dy_all.n) IDD_CUDA(m->dy_all.ensure(Tt));
+  if (Tt > m->y_all.n) { IDD_CUDA(m->y_all.ensure(Tt)); ++m->ws_gen; }
+  if (Tt > m->dy_all.n) { IDD_CUDA(m->dy_all.ensure(Tt)); ++m->ws_gen; }
   const size_t bs = bce_scratch_elems((int64_t)Tt);
-  if (bs > m->small_ws.n) IDD_CUDA(m->small_ws.ensure(bs));
+  if (bs > m->small_ws.n) { IDD_CUDA(m->small_ws.ensure(bs)); ++m->ws_gen; }
+  // hub rows of a power-law graph need a split-pass workspace; size it now, a capture could not allocate it
+  IDD_TRY(spmm_prepare(g, m->D, st));
   // the tensor-core GEMM allocates its weight-split scratch lazily, which a stream capture would forbid
   if ((m->D == 64 || m->D == 128) && (m->N >= 32768 || 2 * b->T >= 32768) && tc_gemm_enabled())
     IDD_TRY(tc_gemm_prepare(st));
@@ -383,7 +402,18 @@ int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p) {
       ++i;
     }
   }
-  if (m->graph_exec && (m->graph_key[1] == p || m->graph_key[2] == p)) {
+  if (m->graph_exec && (m->graph_uid[1] == p->uid || m->graph_uid[2] == p->uid)) {
+    cudaGraphExecDestroy(m->graph_exec);
+    m->graph_exec = nullptr;
+  }
+  return IDDGCN_OK;
+}
+
+// drop the captured train step if it was captured on this graph (Graph.close calls this before destroying it)
+int iddgcn_model_release_graph(iddgcn_model_t* m, const iddgcn_graph_t* g) {
+  IDD_CHECK(m != nullptr, IDDGCN_EINVAL, "model is NULL");
+  if (m->graph_exec && g && m->graph_uid[0] == g->uid) {
+    cudaDeviceSynchronize();
     cudaGraphExecDestroy(m->graph_exec);
     m->graph_exec = nullptr;
   }
@@ -402,6 +432,16 @@ int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgc
   IDD_TRY(triple_forward(m, p, w, w->y, st));
   if (y && p->T) IDD_CUDA(cudaMemcpyAsync(y, w->y, (size_t)p->T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return IDDGCN_OK;
+}
+
+// DLPack flavour of iddgcn_model_forward: vals_dl (NULL for the unweighted adjacency) [nnz], y_dl [T]
+int iddgcn_model_forward_dl(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, void* vals_dl,
+                            int vals_mode, void* y_dl, void* stream) {
+  IDD_TRY(check_compat(m, g, p));
+  float *vals = nullptr, *y = nullptr;
+  if (vals_dl) IDD_TRY(dl_f32_shaped(vals_dl, "vals", m->device, g->nnz, "[nnz]", &vals));
+  IDD_TRY(dl_f32_shaped(y_dl, "y", m->device, p->T, "[T]", &y));
+  return iddgcn_model_forward(m, g, p, vals, vals_mode, y, stream);
 }
 
 int iddgcn_model_backward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, const float* vals,
@@ -451,7 +491,9 @@ int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
   const int64_t t0 = first_step_index - 1;  // the graph increments the counter before Adam reads it
   IDD_CUDA(cudaMemcpyAsync(m->step_dev, &t0, sizeof(int64_t), cudaMemcpyHostToDevice, st));
   IDD_CUDA(cudaStreamSynchronize(st));
-  const bool same = m->graph_exec && m->graph_key[0] == g && m->graph_key[1] == pos && m->graph_key[2] == neg &&
+  const uint64_t neg_uid = neg ? neg->uid : 0;
+  const bool same = m->graph_exec && m->graph_uid[0] == g->uid && m->graph_uid[1] == pos->uid &&
+                    m->graph_uid[2] == neg_uid && m->graph_gen == m->ws_gen && m->graph_heavy_ws == g->heavy_ws &&
                     m->graph_hyper[0] == lr && m->graph_hyper[1] == beta1 && m->graph_hyper[2] == beta2 &&
                     m->graph_hyper[3] == eps;
   if (!same) {
@@ -465,7 +507,9 @@ int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
     ce = cudaGraphInstantiate(&m->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     IDD_CUDA(ce);
-    m->graph_key[0] = g; m->graph_key[1] = pos; m->graph_key[2] = neg;
+    m->graph_uid[0] = g->uid; m->graph_uid[1] = pos->uid; m->graph_uid[2] = neg_uid;
+    m->graph_gen = m->ws_gen;
+    m->graph_heavy_ws = g->heavy_ws;
     m->graph_hyper[0] = lr; m->graph_hyper[1] = beta1; m->graph_hyper[2] = beta2; m->graph_hyper[3] = eps;
   }
   for (int64_t i = 0; i < num_steps; ++i) {
@@ -584,6 +628,50 @@ int iddgcn_layer_bwd(const iddgcn_plan_t* p, const float* HT_in, const float* HT
   IDD_TRY(layer_bwd_post(dz.p, W_alpha, T, D, R, dHT_in, st));
   IDD_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
   return IDDGCN_OK;
+}
+
+// DLPack flavour of the two layer entry points.  Every tensor is a DLManagedTensor* (float32, CUDA, compact):
+//   HT_in / HT_out / dHT_out / dHT_in [2,T,D] (head plane, tail plane), Z / dZ [R,N,D], W_self / dW_self [D,D],
+//   W_alpha / dW_alpha [D,R], b_alpha / db_alpha [R], alpha [T,R].  D is read from W_self.
+int iddgcn_layer_fwd_dl(const iddgcn_plan_t* p, void* HT_in_dl, void* Z_dl, void* W_self_dl, void* W_alpha_dl,
+                        void* b_alpha_dl, void* HT_out_dl, void* alpha_out_dl, void* stream) {
+  IDD_CHECK(p != nullptr, IDDGCN_EINVAL, "plan is NULL");
+  float *ws = nullptr, *hin, *z, *wa, *ba, *hout, *al;
+  int64_t n = 0, D = 0;
+  IDD_TRY(dl_f32_cuda(W_self_dl, "W_self", p->device, &ws, &n, &D));
+  IDD_CHECK(n == D * D, IDDGCN_EINVAL, "W_self must be [D,D]");
+  const int64_t T = p->T, R = p->R;
+  IDD_TRY(dl_f32_shaped(HT_in_dl, "HT_in", p->device, 2 * T * D, "[2,T,D]", &hin));
+  IDD_TRY(dl_f32_shaped(Z_dl, "Z", p->device, R * p->N * D, "[R,N,D]", &z));
+  IDD_TRY(dl_f32_shaped(W_alpha_dl, "W_alpha", p->device, D * R, "[D,R]", &wa));
+  IDD_TRY(dl_f32_shaped(b_alpha_dl, "b_alpha", p->device, R, "[R]", &ba));
+  IDD_TRY(dl_f32_shaped(HT_out_dl, "HT_out", p->device, 2 * T * D, "[2,T,D]", &hout));
+  IDD_TRY(dl_f32_shaped(alpha_out_dl, "alpha", p->device, T * R, "[T,R]", &al));
+  return iddgcn_layer_fwd(p, nullptr, hin, hin + (size_t)T * D, z, ws, wa, ba, D, hout, hout + (size_t)T * D, al,
+                          stream);
+}
+
+int iddgcn_layer_bwd_dl(const iddgcn_plan_t* p, void* HT_in_dl, void* HT_out_dl, void* alpha_dl, void* Z_dl,
+                        void* W_self_dl, void* W_alpha_dl, void* dHT_out_dl, void* dHT_in_dl, void* dZ_dl,
+                        int accumulate_dZ, void* dW_self_dl, void* dW_alpha_dl, void* db_alpha_dl, void* stream) {
+  IDD_CHECK(p != nullptr, IDDGCN_EINVAL, "plan is NULL");
+  float *ws = nullptr, *hin, *hout, *al, *z, *wa, *dho, *dhi, *dz, *dws, *dwa, *dba;
+  int64_t n = 0, D = 0;
+  IDD_TRY(dl_f32_cuda(W_self_dl, "W_self", p->device, &ws, &n, &D));
+  IDD_CHECK(n == D * D, IDDGCN_EINVAL, "W_self must be [D,D]");
+  const int64_t T = p->T, R = p->R;
+  IDD_TRY(dl_f32_shaped(HT_in_dl, "HT_in", p->device, 2 * T * D, "[2,T,D]", &hin));
+  IDD_TRY(dl_f32_shaped(HT_out_dl, "HT_out", p->device, 2 * T * D, "[2,T,D]", &hout));
+  IDD_TRY(dl_f32_shaped(alpha_dl, "alpha", p->device, T * R, "[T,R]", &al));
+  IDD_TRY(dl_f32_shaped(Z_dl, "Z", p->device, R * p->N * D, "[R,N,D]", &z));
+  IDD_TRY(dl_f32_shaped(W_alpha_dl, "W_alpha", p->device, D * R, "[D,R]", &wa));
+  IDD_TRY(dl_f32_shaped(dHT_out_dl, "dHT_out", p->device, 2 * T * D, "[2,T,D]", &dho));
+  IDD_TRY(dl_f32_shaped(dHT_in_dl, "dHT_in", p->device, 2 * T * D, "[2,T,D]", &dhi));
+  IDD_TRY(dl_f32_shaped(dZ_dl, "dZ", p->device, R * p->N * D, "[R,N,D]", &dz));
+  IDD_TRY(dl_f32_shaped(dW_self_dl, "dW_self", p->device, D * D, "[D,D]", &dws));
+  IDD_TRY(dl_f32_shaped(dW_alpha_dl, "dW_alpha", p->device, D * R, "[D,R]", &dwa));
+  IDD_TRY(dl_f32_shaped(db_alpha_dl, "db_alpha", p->device, R, "[R]", &dba));
+  return iddgcn_layer_bwd(p, hin, hout, al, z, ws, wa, D, dho, dhi, dz, accumulate_dZ, dws, dwa, dba, stream);
 }
 
 // out[plane][n][:] (+)= segment sums of dHT (2,T,D) by head and by tail; alpha NULL -> one plane, weight 1

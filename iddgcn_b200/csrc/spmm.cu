@@ -12,6 +12,7 @@
 // atomics and the summation order is fixed (ascending neighbour index, as TF-CPU does).
 // Edge weights (explicit values or sigmoid(mask)) are applied in registers.
 #include <stdlib.h>
+#include "dlpack.cuh"
 #include "graph.cuh"
 
 namespace iddgcn {
@@ -30,10 +31,16 @@ struct AddSrcs {
 static inline AddSrcs add_none() { AddSrcs a{}; a.n = 0; return a; }
 static inline AddSrcs add_self(const float* out) { AddSrcs a{}; a.n = 1; a.p[0] = out; return a; }
 
+// statically indexed (fully unrolled, predicated): a run-time index into the by-value parameter struct would make the
+// compiler copy it to local memory and spill around every flush
 __device__ __forceinline__ void add_rows(float4& r, const AddSrcs& add, size_t vec_index) {
-  for (int j = 0; j < add.n; ++j) {
-    const float4 prev = *(reinterpret_cast<const float4*>(add.p[j]) + vec_index);
-    r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+  if (add.n == 0) return;
+#pragma unroll
+  for (int j = 0; j < MAX_ADD; ++j) {
+    if (j < add.n) {
+      const float4 prev = *(reinterpret_cast<const float4*>(add.p[j]) + vec_index);
+      r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+    }
   }
 }
 
@@ -143,7 +150,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
 // backward: ptr=bwd_rowptr, idx=bwd_src,  src=dS as [(R·n_rows),D], weight index perm[e]
 constexpr int SLAB = 512;  // staged indices per warp
 
-template <int LPR, int U, int MODE, bool USE_PERM, bool HUBS, int TPB = SPMM_THREADS, int MINB = 4, bool NA = false>
+template <int LPR, int U, int MODE, bool USE_PERM, bool HUBS, int TPB = SPMM_THREADS, int MINB = 4, bool NA = false,
+          bool ADD = false>
 __global__ void __launch_bounds__(TPB, MINB)
     stream_rows_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                        const int32_t* __restrict__ perm, const float* __restrict__ vals,
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        add_rows(r, add, (size_t)(r0 + row) * nvec + l);
+        if constexpr (ADD) add_rows(r, add, (size_t)(r0 + row) * nvec + l);
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        add_rows(r, add, (size_t)(r0 + row) * nvec + l);
+        if constexpr (ADD) add_rows(r, add, (size_t)(r0 + row) * nvec + l);
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -777,14 +785,21 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   constexpr int rows_per_block = (SPMM_THREADS / 32) * 32;  // every warp covers 32 rows (SUBS chunks of LPR)
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
-#define IDD_STREAM(MODE_)                                                                                     \
-  do {                                                                                                        \
-    if (a.heavy_t == 0x7fffffff)                                                                              \
-      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, false><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(          \
-          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t); \
-    else                                                                                                      \
-      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, true><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(           \
-          a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t); \
+  // the epilogue addends (accumulate / staged peer partials) exist only on the backward side (USE_PERM) and are a
+  // separate instantiation, so the plain kernels keep the register allocation they were tuned with (64, no spills)
+#define IDD_STREAM_ARGS a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t
+#define IDD_STREAM2(MODE_, HUBS_)                                                                                    \
+  do {                                                                                                               \
+    if (USE_PERM && a.add.n > 0)                                                                                     \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_, SPMM_THREADS, 4, false, USE_PERM>                           \
+          <<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS);                                              \
+    else                                                                                                             \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS); \
+  } while (0)
+#define IDD_STREAM(MODE_)                                       \
+  do {                                                          \
+    if (a.heavy_t == 0x7fffffff) IDD_STREAM2(MODE_, false);     \
+    else IDD_STREAM2(MODE_, true);                              \
   } while (0)
   // IDDGCN_TUNE=<k>: launch-shape variants of the headline instantiation (D=128, unweighted, no hub rows) for A/B runs
   if (LPR == 32 && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff) {
@@ -821,6 +836,8 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   else if (mode == IDDGCN_VALS_EXPLICIT) IDD_STREAM(IDDGCN_VALS_EXPLICIT);
   else IDD_STREAM(IDDGCN_VALS_SIGMOID);
 #undef IDD_STREAM
+#undef IDD_STREAM2
+#undef IDD_STREAM_ARGS
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }
@@ -993,19 +1010,22 @@ int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64
   if (g->nnz == 0) return IDDGCN_OK;
   const int nvec = (int)(D / 4);
   if (D <= 128 && !use_v1((int64_t)g->R * g->n_rows)) {
-    if (nvec <= 4) return launch_sddmm_stream<4, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
-    if (nvec <= 8) return launch_sddmm_stream<8, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
-    if (nvec <= 16) return launch_sddmm_stream<16, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+    // launch shape measured at config 3 (profiles/r02_sddmm_launch_shape_sweep.txt): occupancy beats batch depth —
+    // U=4 gathers in flight with 5 blocks/SM (48 registers) 2.48 ms, U=4 x 4 blocks 2.81, U=8 x 3 blocks 3.63,
+    // U=8 x 2 blocks 4.97 ms
+    if (nvec <= 4) return launch_sddmm_stream<4, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 8) return launch_sddmm_stream<8, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 16) return launch_sddmm_stream<16, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
     if (const char* tv = getenv("IDDGCN_SDDMM_TUNE")) {   // launch-shape variants of the D=128 instantiation (A/B runs)
       switch (atoi(tv)) {
-        case 1: return launch_sddmm_stream<32, 8, 2>(g, dS, X, vals, mode, dvals, nvec, st);
-        case 2: return launch_sddmm_stream<32, 4, 4>(g, dS, X, vals, mode, dvals, nvec, st);
-        case 3: return launch_sddmm_stream<32, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
-        case 4: return launch_sddmm_stream<32, 8, 4>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 1: return launch_sddmm_stream<32, 4, 6>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 2: return launch_sddmm_stream<32, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 3: return launch_sddmm_stream<32, 4, 4>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 4: return launch_sddmm_stream<32, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
         default: break;
       }
     }
-    return launch_sddmm_stream<32, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
+    return launch_sddmm_stream<32, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
   }
   if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
   if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
@@ -1198,46 +1218,7 @@ int iddgcn_spmm_fwd_bwd_host(const iddgcn_graph_t* g, const float* X_host, const
   return rc;
 }
 
-// ---- DLPack flavour ------------------------------------------------------------------------
-// dlpack.h (v0.x) ABI, restated so that no third-party header is needed.
-typedef struct { int32_t device_type; int32_t device_id; } idd_DLDevice;
-typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } idd_DLDataType;
-typedef struct {
-  void* data; idd_DLDevice device; int32_t ndim; idd_DLDataType dtype; int64_t* shape; int64_t* strides;
-  uint64_t byte_offset;
-} idd_DLTensor;
-typedef struct idd_DLManagedTensor {
-  idd_DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct idd_DLManagedTensor*);
-} idd_DLManagedTensor;
-
-static int dl_f32_cuda(void* capsule_ptr, const char* name, int device, float** data, int64_t* numel,
-                       int64_t* last_dim) {
-  IDD_CHECK(capsule_ptr != nullptr, IDDGCN_EINVAL, "%s: NULL DLManagedTensor", name);
-  const idd_DLTensor& t = reinterpret_cast<idd_DLManagedTensor*>(capsule_ptr)->dl_tensor;
-  IDD_CHECK(t.device.device_type == 2 /*kDLCUDA*/, IDDGCN_EINVAL,
-            "%s: DLPack tensor is not on a CUDA device (device_type=%d); there is no CPU path", name,
-            t.device.device_type);
-  IDD_CHECK(t.device.device_id == device, IDDGCN_EINVAL, "%s: tensor on cuda:%d but handle on cuda:%d", name,
-            t.device.device_id, device);
-  IDD_CHECK(t.dtype.code == 2 && t.dtype.bits == 32 && t.dtype.lanes == 1, IDDGCN_EINVAL, "%s: dtype must be float32",
-            name);
-  IDD_CHECK(t.ndim >= 1, IDDGCN_EINVAL, "%s: ndim must be >= 1", name);
-  int64_t n = 1;
-  for (int i = 0; i < t.ndim; ++i) n *= t.shape[i];
-  if (t.strides) {
-    int64_t expect = 1;
-    for (int i = t.ndim - 1; i >= 0; --i) {
-      IDD_CHECK(t.shape[i] == 1 || t.strides[i] == expect, IDDGCN_EINVAL, "%s: tensor must be compact row-major",
-                name);
-      expect *= t.shape[i];
-    }
-  }
-  *data = reinterpret_cast<float*>(reinterpret_cast<char*>(t.data) + t.byte_offset);
-  *numel = n;
-  *last_dim = t.shape[t.ndim - 1];
-  return IDDGCN_OK;
-}
-
+// ---- DLPack flavour (argument unpacking: dlpack.cuh) ----------------------------------------
 int iddgcn_spmm_fwd_dl(const iddgcn_graph_t* g, void* X_dl, void* vals_dl, int vals_mode, void* S_dl, void* stream) {
   IDD_CHECK(g != nullptr, IDDGCN_EINVAL, "graph is NULL");
   float *X, *S, *vals = nullptr;

@@ -66,10 +66,15 @@ class Graph:
         self.nnz_per_rel = [int(x) for x in per]
         self.rel_offsets = np.concatenate([[0], np.cumsum(self.nnz_per_rel)]).astype(np.int64)
         self._dev_cache = {}
+        self._models = []              # weak refs to models that captured a train step on this graph
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            for ref in getattr(self, "_models", []):
+                m = ref()
+                if m is not None and getattr(m, "_h", None):
+                    self._lib.iddgcn_model_release_graph(m._h, self._h)
             self._lib.iddgcn_graph_destroy(self._h)
             self._h = None
 

@@ -166,6 +166,17 @@ int iddgcn_spmm_fwd_dl(const iddgcn_graph_t* g, void* X_dl, void* vals_dl, int v
                        void* S_dl, void* stream);
 int iddgcn_spmm_bwd_x_dl(const iddgcn_graph_t* g, void* dS_dl, void* vals_dl, int vals_mode,
                          void* dX_dl, int accumulate, void* stream);
+/* DLPack flavours of the layer / model entry points declared further down (same arithmetic, same reference lines:
+ * IDDGCN.py:60-79 and IDDGCN.py:147-153); tensor shapes: HT_* / dHT_* [2,T,D] (head plane then tail plane),
+ * Z / dZ [R,N,D], W_self / dW_self [D,D], W_alpha / dW_alpha [D,R], b_alpha / db_alpha [R], alpha [T,R], vals [nnz]
+ * or NULL, y [T].  D is read from W_self; every shape is validated against the plan / graph / model handle. */
+int iddgcn_layer_fwd_dl(const iddgcn_plan_t* p, void* HT_in_dl, void* Z_dl, void* W_self_dl, void* W_alpha_dl,
+                        void* b_alpha_dl, void* HT_out_dl, void* alpha_out_dl, void* stream);
+int iddgcn_layer_bwd_dl(const iddgcn_plan_t* p, void* HT_in_dl, void* HT_out_dl, void* alpha_dl, void* Z_dl,
+                        void* W_self_dl, void* W_alpha_dl, void* dHT_out_dl, void* dHT_in_dl, void* dZ_dl,
+                        int accumulate_dZ, void* dW_self_dl, void* dW_alpha_dl, void* db_alpha_dl, void* stream);
+int iddgcn_model_forward_dl(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, void* vals_dl,
+                            int vals_mode, void* y_dl, void* stream);
 
 /* ------------------------------------------------------------------------
  * Triple plan — the per-call index structure the triple stage needs:
@@ -276,6 +287,9 @@ int iddgcn_model_param_layout(const iddgcn_model_t* m, int64_t* offsets, int64_t
 int iddgcn_model_buffers(iddgcn_model_t* m, float** params, float** grads, float** adam_m, float** adam_v);
 /* drop activations cached for a plan (call before destroying the plan) */
 int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p);
+/* drop the train step captured on graph g (call before destroying g).  The captured step is keyed on unique handle
+ * ids and on a workspace generation counter, so a recycled heap address or a regrown workspace never replays it. */
+int iddgcn_model_release_graph(iddgcn_model_t* m, const iddgcn_graph_t* g);
 /* y [T] = model(head, rel, tail | graph, optional edge vals)   (IDDGCN.py:147-153, IDDGCN_eval.py:97-105) */
 int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p,
                          const float* vals, int vals_mode, float* y, void* stream);

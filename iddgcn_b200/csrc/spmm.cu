@@ -1011,21 +1011,21 @@ int sddmm_dispatch(const iddgcn_graph* g, const float* dS, const float* X, int64
   const int nvec = (int)(D / 4);
   if (D <= 128 && !use_v1((int64_t)g->R * g->n_rows)) {
     // launch shape measured at config 3 (profiles/r02_sddmm_launch_shape_sweep.txt): occupancy beats batch depth —
-    // U=4 gathers in flight with 5 blocks/SM (48 registers) 2.48 ms, U=4 x 4 blocks 2.81, U=8 x 3 blocks 3.63,
-    // U=8 x 2 blocks 4.97 ms
-    if (nvec <= 4) return launch_sddmm_stream<4, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
-    if (nvec <= 8) return launch_sddmm_stream<8, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
-    if (nvec <= 16) return launch_sddmm_stream<16, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
+    // (U gathers in flight, blocks/SM): (2,8) 2.02 ms, (4,6) 2.35, (4,5) 2.54, (4,4) 2.76, (8,3) 3.55, (8,2) 4.97 ms.
+    // 8 blocks x 256 threads is the SM's thread limit (32 registers per thread).
+    if (nvec <= 4) return launch_sddmm_stream<4, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 8) return launch_sddmm_stream<8, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+    if (nvec <= 16) return launch_sddmm_stream<16, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
     if (const char* tv = getenv("IDDGCN_SDDMM_TUNE")) {   // launch-shape variants of the D=128 instantiation (A/B runs)
       switch (atoi(tv)) {
         case 1: return launch_sddmm_stream<32, 4, 6>(g, dS, X, vals, mode, dvals, nvec, st);
-        case 2: return launch_sddmm_stream<32, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
+        case 2: return launch_sddmm_stream<32, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
         case 3: return launch_sddmm_stream<32, 4, 4>(g, dS, X, vals, mode, dvals, nvec, st);
         case 4: return launch_sddmm_stream<32, 8, 3>(g, dS, X, vals, mode, dvals, nvec, st);
         default: break;
       }
     }
-    return launch_sddmm_stream<32, 4, 5>(g, dS, X, vals, mode, dvals, nvec, st);
+    return launch_sddmm_stream<32, 2, 8>(g, dS, X, vals, mode, dvals, nvec, st);
   }
   if (nvec <= 8) return launch_sddmm_mode<8, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);
   if (nvec <= 16) return launch_sddmm_mode<16, 1, 8>(g, dS, X, vals, mode, dvals, nvec, st);

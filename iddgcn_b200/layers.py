@@ -37,10 +37,11 @@ class _PlanCache:
             a = x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
             return ("h", a.size, hash(np.ascontiguousarray(a).tobytes()))
         key = (key_of(head_idx), key_of(rel_idx), key_of(tail_idx))
-        p = self._c.get(key)
+        ent = self._c.get(key)
+        p = ent[0] if ent is not None else None
         if p is None:
             if len(self._c) >= 32:
-                self._c.pop(next(iter(self._c))).close()
+                self._c.pop(next(iter(self._c)))[0].close()
             ref = head_idx if head_idx is not None else rel_idx
             T = int(ref.numel() if isinstance(ref, torch.Tensor) else np.asarray(ref).size)
             dev = ref.device if isinstance(ref, torch.Tensor) and ref.is_cuda else None
@@ -48,7 +49,8 @@ class _PlanCache:
             p = Plan(head_idx if head_idx is not None else zeros, rel_idx if rel_idx is not None else zeros,
                      tail_idx if tail_idx is not None else zeros, self.N, self.R,
                      device=dev)
-            self._c[key] = p
+            # device tensors are keyed by address: keep them alive with the entry so the address cannot be recycled
+            self._c[key] = (p, [x for x in (head_idx, rel_idx, tail_idx) if isinstance(x, torch.Tensor) and x.is_cuda])
         return p
 
 

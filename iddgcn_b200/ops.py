@@ -117,6 +117,31 @@ def spmm_bwd_x_dlpack(graph: Graph, dS, dX, vals=None, mode: int = VALS_ONES, ac
                                       int(accumulate), stream))
 
 
+def layer_fwd_dlpack(plan, HT_in, Z, W_self, W_alpha, b_alpha, HT_out, alpha_out) -> None:
+    """iddgcn_layer_fwd with every tensor crossing the boundary as a DLPack capsule (IDDGCN.py:60-79)."""
+    ts = [HT_in, Z, W_self, W_alpha, b_alpha, HT_out, alpha_out]
+    caps = [t.__dlpack__() for t in ts]
+    check(load().iddgcn_layer_fwd_dl(plan.handle, *[_dl_ptr(c) for c in caps],
+                                     torch.cuda.current_stream(HT_in.device).cuda_stream))
+
+
+def layer_bwd_dlpack(plan, HT_in, HT_out, alpha, Z, W_self, W_alpha, dHT_out, dHT_in, dZ, dW_self, dW_alpha, db_alpha,
+                     accumulate_dZ: bool = False) -> None:
+    """iddgcn_layer_bwd through DLPack capsules; weight gradients are accumulated into dW_self / dW_alpha / db_alpha."""
+    a = [t.__dlpack__() for t in (HT_in, HT_out, alpha, Z, W_self, W_alpha, dHT_out, dHT_in, dZ)]
+    b = [t.__dlpack__() for t in (dW_self, dW_alpha, db_alpha)]
+    check(load().iddgcn_layer_bwd_dl(plan.handle, *[_dl_ptr(c) for c in a], int(accumulate_dZ),
+                                     *[_dl_ptr(c) for c in b], torch.cuda.current_stream(HT_in.device).cuda_stream))
+
+
+def model_forward_dlpack(model, graph: Graph, plan, y, vals=None, mode: int = VALS_ONES) -> None:
+    """iddgcn_model_forward through DLPack capsules: y [T] <- model(triples of `plan` | graph, optional edge values)."""
+    cy = y.__dlpack__()
+    cv = vals.__dlpack__() if vals is not None else None
+    check(load().iddgcn_model_forward_dl(model._h, graph.handle, plan.handle, _dl_ptr(cv) if cv is not None else None,
+                                         mode, _dl_ptr(cy), torch.cuda.current_stream(graph.device).cuda_stream))
+
+
 def spmm_fwd_bwd_host(graph: Graph, X_host: torch.Tensor, dS_host: torch.Tensor, S_host=None, dX_host=None):
     """End-to-end call with HOST buffers (pinned recommended): upload, fwd, bwd, download."""
     for t, n in ((X_host, "X_host"), (dS_host, "dS_host")):

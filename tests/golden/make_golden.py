@@ -11,6 +11,8 @@ The GPU box has no /root/reference, so everything a test needs from it is frozen
   h5_sample_fold4.h5      one original .h5 (parser fixture)
   metrics.json            SURVEY Appendix D fold metrics, recomputed here with the oracle in fp64 and fp32
   preds_fold{1,4}.npz     oracle fp64 predictions / pre-sigmoid logits for the eval triples of folds 1 and 4
+  explaiNE_preds_fold4.npz  the shipped explaiNE predictions (288,10,3) + scores (288,10), int16 / float32 re-encoding
+                          (explanation/explaiNE.py:98); structural pin only (the weights behind it are not shipped)
   gt_all.npz              the shipped explanation ground-truth table (datasets/explanation_datasets/gt_all.csv, written by
                           explanation/ground_truth.py) as ragged int16 rows: `flat` + `offsets` — the known answer for
                           oracle.construct_ground_truth; only the CSV is read (the shipped *.npz files are pickled
@@ -50,6 +52,14 @@ def main(ref="/root/reference"):
     assert np.array_equal(flat, flat.astype(np.int16)), "ground-truth ids no longer fit int16"
     np.savez_compressed(os.path.join(HERE, "gt_all.npz"), flat=flat.astype(np.int16),
                         offsets=np.cumsum([0] + [len(r) for r in rows]).astype(np.int32))
+
+    # shipped explaiNE output (plain int64 / float32 arrays, no pickle): produced from weights the reference does not
+    # ship, so it pins no values — but every prediction must be an edge of the train+test adjacency whose row is the
+    # head or the tail of the explained triple (1-hop receptive field), scores positive and descending
+    z = np.load(os.path.join(ex_dir, "explaiNE_preds_fold4.npz"), allow_pickle=False)
+    assert np.array_equal(z["preds"], z["preds"].astype(np.int16))
+    np.savez_compressed(os.path.join(HERE, "explaiNE_preds_fold4.npz"), preds=z["preds"].astype(np.int16),
+                        scores=z["scores"].astype(np.float32))
 
     hashes = {}
     for f in range(5):

@@ -317,3 +317,113 @@ def test_dense_mask_product_and_fit_callbacks(tmp_path):
     assert not np.array_equal(h5.read_weight_list(tmp_path / "w2.h5")[0], m.get_weights()[0])
     emb = m.get_layer("entity_embeddings").get_weights()[0]
     assert emb.shape == (N, D) and len(m.trainable_weights) == 17
+
+
+def test_fit_on_hub_graph_and_graph_reuse_after_workspace_regrow():
+    """(i) model.fit() on a FRESH graph with hub rows (the split-pass workspace must exist before the
+    step is captured); (ii) a forward on a larger plan between two fit() chunks regrows shared workspaces — the
+    captured step must be re-captured, not replayed with stale pointers; (iii) a new graph object never replays the
+    step captured on a destroyed one.  All against the eager (uncaptured) train_step trajectory."""
+    from iddgcn_b200 import Adam, get_adj_mats
+    N, R, D = 3000, 2, 64
+    rng = np.random.default_rng(4)
+    tri = random_triples(N, R, 30000, seed=4, heavy_row=5)          # row 5: ~7.5k edges -> ~2.7k distinct tails: a hub
+    hub_col = tri[:4000].copy(); hub_col[:, 2] = 9                  # hub on the backward side too
+    tri = np.concatenate([tri, hub_col], 0)
+    pos = tri[rng.permutation(len(tri))[:900]]
+    neg = np.stack([rng.integers(0, N, 100), rng.integers(0, R, 100), rng.integers(0, N, 100)], 1).astype(np.int64)
+    p = _round32(O.init_params(N, R, D, 3, seed=9, scale=0.05))
+    x_of = lambda adj: [np.arange(N).reshape(1, -1), pos[None, :, 0], pos[None, :, 1], pos[None, :, 2], adj]
+    # eager trajectory: 6 steps
+    m1 = _model_for(p, N, R, D)
+    adj1 = get_adj_mats(tri, N, R)
+    l1 = [float(m1.train_step((x_of(adj1), None), neg_triples=neg)) for _ in range(6)]
+    # captured: 2 steps, then a bigger forward (regrows gemm_ws / small_ws), 2 more steps, then a NEW graph object
+    m2 = _model_for(p, N, R, D)
+    m2.compile(optimizer=Adam(learning_rate=1e-3))
+    adj2 = get_adj_mats(tri, N, R)                                  # fresh graph: hub workspace not yet allocated
+    h = m2.fit(x=x_of(adj2), epochs=2, verbose=0, neg_triples=neg).history["loss"]
+    big = tri[: 20000]
+    m2.predict([np.arange(N).reshape(1, -1), big[None, :, 0], big[None, :, 1], big[None, :, 2], adj2])
+    h += m2.fit(x=x_of(adj2), epochs=2, verbose=0, neg_triples=neg).history["loss"]
+    adj2[0].graph.close()
+    adj3 = get_adj_mats(tri, N, R)
+    h += m2.fit(x=x_of(adj3), epochs=2, verbose=0, neg_triples=neg).history["loss"]
+    assert np.allclose(h, l1, rtol=1e-5, atol=0), (h, l1)
+    for a, b in zip(m1.get_weights(), m2.get_weights()):
+        assert np.array_equal(a, b)
+
+
+def test_plan_cache_is_not_fooled_by_recycled_device_addresses():
+    """fresh device index tensors per call get the address of the previous (freed) ones from the caching
+    allocator; the model must score THESE triples, not the cached plan of the previous call."""
+    from iddgcn_b200 import get_adj_mats
+    N, R, D = 200, 3, 64
+    tri, pos, _, p = _setup(N, R, D, 2000, 300, 5, seed=3)
+    m = _model_for(p, N, R, D)
+    adj = get_adj_mats(tri, N, R)
+    adj_o = O.get_adj_mats(tri, N, R)
+    rng = np.random.default_rng(0)
+    ptrs = set()
+    for it in range(4):
+        sel = pos[rng.permutation(len(pos))[:128]]
+        h, r, t = (torch.from_numpy(sel[:, k].copy()).cuda() for k in range(3))
+        ptrs.add(h.data_ptr())
+        y = m([torch.arange(N)[None], h[None], r[None], t[None], adj])[0].cpu().numpy()
+        y_ref = O.model_forward(p, adj_o, sel[:, 0], sel[:, 1], sel[:, 2])
+        assert rel_err(y, np.asarray(y_ref).reshape(-1)) < FWD_TOL, it
+        del h, r, t
+
+
+def test_dlpack_layer_and_model_entry_points():
+    """north_star: "C-ABI layer with DLPack tensor exchange" — the layer forward / backward and the model forward
+    taking DLManagedTensor* give bit-identical results to the raw-pointer entry points, and validate shapes."""
+    from iddgcn_b200 import _lib, get_adj_mats, ops
+    from iddgcn_b200._lib import IddgcnError, check, load, ptr
+    from iddgcn_b200.plan import Plan
+    lib = load()
+    N, R, D, T = 90, 3, 64, 150
+    tri, pos, _, p = _setup(N, R, D, 1500, T, 5, seed=12, scale=0.1)
+    T = len(pos)
+    adj = get_adj_mats(tri, N, R)
+    g = adj[0].graph
+    plan = Plan(pos[:, 0], pos[:, 1], pos[:, 2], N, R, device=g.device)
+    f = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32, device="cuda").contiguous()
+    lp = p.layers[0]
+    emb, rk, sk, wa, ba = f(p.emb), f(lp.relation_kernels), f(lp.self_kernel), f(lp.W_alpha), f(lp.b_alpha)
+    S = ops.spmm_fwd(g, emb)
+    Z = torch.empty_like(S)
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.iddgcn_relation_transform(ptr(S), ptr(rk), R, N, D, ptr(Z), st))
+    h_idx, t_idx = torch.from_numpy(pos[:, 0].copy()).cuda(), torch.from_numpy(pos[:, 2].copy()).cuda()
+    HT_in = torch.stack([emb[h_idx], emb[t_idx]], 0).contiguous()
+    out_a, out_b = torch.empty_like(HT_in), torch.empty_like(HT_in)
+    al_a, al_b = torch.empty((T, R), device="cuda"), torch.empty((T, R), device="cuda")
+    check(lib.iddgcn_layer_fwd(plan.handle, None, ptr(HT_in[0]), ptr(HT_in[1]), ptr(Z), ptr(sk), ptr(wa), ptr(ba), D,
+                               ptr(out_a[0]), ptr(out_a[1]), ptr(al_a), st))
+    ops.layer_fwd_dlpack(plan, HT_in, Z, sk, wa, ba, out_b, al_b)
+    assert torch.equal(out_a, out_b) and torch.equal(al_a, al_b)
+    dH = torch.randn_like(HT_in)
+    res = []
+    for use_dl in (False, True):
+        dho, dhi, dZ = dH.clone(), torch.empty_like(HT_in), torch.empty_like(Z)
+        dsk, dwa, dba = torch.zeros_like(sk), torch.zeros_like(wa), torch.zeros(R, device="cuda")
+        if use_dl:
+            ops.layer_bwd_dlpack(plan, HT_in, out_a, al_a, Z, sk, wa, dho, dhi, dZ, dsk, dwa, dba)
+        else:
+            check(lib.iddgcn_layer_bwd(plan.handle, ptr(HT_in), ptr(out_a), ptr(al_a), ptr(Z), ptr(sk), ptr(wa), D,
+                                       ptr(dho), ptr(dhi), ptr(dZ), 0, ptr(dsk), ptr(dwa), ptr(dba), st))
+        res.append((dho, dhi, dZ, dsk, dwa, dba))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    with pytest.raises(IddgcnError):                       # wrong shape is refused, not read out of bounds
+        ops.layer_fwd_dlpack(plan, HT_in[:, :-1].contiguous(), Z, sk, wa, ba, out_b, al_b)
+    with pytest.raises(IddgcnError):                       # host tensors are refused: there is no CPU path
+        ops.layer_fwd_dlpack(plan, HT_in.cpu(), Z, sk, wa, ba, out_b, al_b)
+    m = _model_for(p, N, R, D)
+    y_a = m.forward_values(g, plan)
+    y_b = torch.empty_like(y_a)
+    ops.model_forward_dlpack(m, g, plan, y_b)
+    assert torch.equal(y_a, y_b)
+    with pytest.raises(IddgcnError):
+        ops.model_forward_dlpack(m, g, plan, torch.empty(T + 1, device="cuda"))

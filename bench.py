@@ -412,7 +412,7 @@ def run_ours(args, wl):
     torch.cuda.empty_cache()
     nnz_local = g.nnz
 
-    eng = GridSpMM(g, D, world, rank, grid, exchange=args.exchange)
+    eng = GridSpMM(g, D, world, rank, grid, exchange=args.exchange, partials=args.partials, order=args.order)
     fill_rows(torch, eng.x_local_view(), "X", row_lo, pc * Dc, D)
     for r in range(R):
         fill_rows(torch, eng.dS[r], "dS", r * N_total + row_lo, pc * Dc, D)
@@ -493,7 +493,7 @@ def run_ours(args, wl):
     kt = eng.kernel_times(iters=max(args.steps, 5))
     comm = None
     if world > 1:
-        comm = {"grid": f"{grid[0]}x{grid[1]}", "exchange": eng.exchange,
+        comm = {"grid": f"{grid[0]}x{grid[1]}", "exchange": eng.exchange, "partials": eng.partials, "order": eng.order,
                 "bytes_exchanged_per_rank_each_way": int((grid[0] - 1) * block * Dc * 4)}
         et = eng.exchange_times(iters=5) if eng.exchange == "p2p" else None
         if et:
@@ -632,6 +632,11 @@ def main():
                                                     "groups (auto: 1x2, 2x2, 2x4 at 2/4/8 GPUs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="row exchange inside a column group: fused peer-memory kernels or NCCL collectives")
+    ap.add_argument("--partials", default="stores", choices=["stores", "dma"],
+                    help="p2p exchange: partial dX rows leave through NVLink stores of the backward kernel (fused) or "
+                         "through the copy engines")
+    ap.add_argument("--order", default="AFB", choices=["AFB", "ABF"],
+                    help="p2p exchange: kernel order inside a step (A peers' backward blocks, F forward, B own block)")
     ap.add_argument("--check-rows", type=int, default=1_000_000,
                     help="rows (over all ranks) of S and of dX compared with the CPU oracle after the timed region")
     args = ap.parse_args()

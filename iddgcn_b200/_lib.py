@@ -70,6 +70,8 @@ _SIGNATURES = {
     "iddgcn_model_buffers": (C.c_int, [vp] + [C.POINTER(vp)] * 4),
     "iddgcn_model_release_plan": (C.c_int, [vp, vp]),
     "iddgcn_model_release_graph": (C.c_int, [vp, vp]),
+    "iddgcn_model_profile": (C.c_int, [vp, C.c_int]),
+    "iddgcn_model_profile_read": (C.c_int, [vp, vp, C.c_int]),
     "iddgcn_model_forward": (C.c_int, [vp, vp, vp, vp, C.c_int, vp, vp]),
     "iddgcn_model_train_step": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                           C.c_int, vp, vp, vp]),

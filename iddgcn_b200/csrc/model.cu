@@ -75,10 +75,35 @@ struct iddgcn_model {
   uint64_t ws_gen = 1;
   cudaStream_t own_stream = nullptr;
 
+  // optional per-group timing of one train step (iddgcn_model_profile): an event after every kernel group
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_tag;
+  size_t prof_n = 0;
+
   float* P(int64_t off) const { return params + off; }
   float* G(int64_t off) const { return grads + off; }
   size_t plane() const { return (size_t)R * N * D; }
 };
+
+// kernel groups of a train step (tools/bench_layer.py holds the byte / flop model of each)
+enum ProfTag {
+  PT_START = 0, PT_ZERO, PT_SPMM_FWD, PT_REL_TRANSFORM, PT_GATHER_EMB, PT_SELF_TRANSFORM, PT_COMBINE, PT_DISTMULT_FWD,
+  PT_BCE, PT_DISTMULT_BWD, PT_BWD_PRE, PT_DW_SELF, PT_DW_ALPHA, PT_SCATTER_DZ, PT_DIN, PT_BWD_POST, PT_SCATTER_EMB,
+  PT_DW_REL, PT_DS, PT_SPMM_BWD, PT_ADAM, PT_COUNT
+};
+
+static void prof_mark(iddgcn_model* m, int tag, cudaStream_t st) {
+  if (!m->prof_on) return;
+  if (m->prof_n == m->prof_ev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    m->prof_ev.push_back(e);
+    m->prof_tag.push_back(0);
+  }
+  m->prof_tag[m->prof_n] = tag;
+  cudaEventRecord(m->prof_ev[m->prof_n++], st);
+}
 
 static int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
 
@@ -104,6 +129,7 @@ static void model_free(iddgcn_model* m) {
   if (!m) return;
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   for (auto& kv : m->ws) kv.second.release();
   for (auto& e : m->merged) plan_destroy_internal(e.both);
   cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v);
@@ -172,9 +198,11 @@ static int check_compat(const iddgcn_model* m, const iddgcn_graph* g, const iddg
 // S = A·E and Z_l = S·W_l for every layer
 static int node_forward(iddgcn_model* m, const iddgcn_graph* g, const float* vals, int mode, cudaStream_t st) {
   IDD_TRY(spmm_fwd_range(g, m->P(m->lay.emb), m->D, vals, mode, m->S, 0, (int64_t)m->R * m->N, st));
+  prof_mark(m, PT_SPMM_FWD, st);
   for (int l = 0; l < m->L; ++l)
     IDD_TRY(gemm_f32(false, false, m->N, m->D, m->D, m->S, m->D, m->N * m->D, m->P(m->lay.layer[l].rk), m->D,
                      m->D * m->D, m->Z + (size_t)l * m->plane(), m->D, m->N * m->D, m->R, false, st));
+  prof_mark(m, PT_REL_TRANSFORM, st);
   return IDDGCN_OK;
 }
 
@@ -182,14 +210,18 @@ static int triple_forward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, fl
   w->owner = p;
   if (p->T == 0) return IDDGCN_OK;
   IDD_TRY(gather_embeddings(p, m->P(m->lay.emb), m->D, w->HT[0], st));
+  prof_mark(m, PT_GATHER_EMB, st);
   for (int l = 0; l < m->L; ++l) {
     const LayerOffsets& lo = m->lay.layer[l];
     IDD_TRY(gemm_f32(false, false, 2 * p->T, m->D, m->D, w->HT[l], m->D, 0, m->P(lo.sk), m->D, 0, w->HT[l + 1], m->D,
                      0, 1, false, st));
+    prof_mark(m, PT_SELF_TRANSFORM, st);
     IDD_TRY(layer_combine(p, w->HT[l], m->Z + (size_t)l * m->plane(), m->P(lo.wa), m->P(lo.ba), m->D, w->HT[l + 1],
                           w->alpha[l], st));
+    prof_mark(m, PT_COMBINE, st);
   }
   IDD_TRY(distmult_fwd(p, w->HT[m->L], m->P(m->lay.rel_emb), m->D, y_out, st));
+  prof_mark(m, PT_DISTMULT_FWD, st);
   return IDDGCN_OK;
 }
 
@@ -201,26 +233,34 @@ static int triple_backward(iddgcn_model* m, const iddgcn_plan* p, TripleWS* w, c
   int cur = 0;
   IDD_TRY(distmult_bwd(p, w->HT[m->L], m->P(m->lay.rel_emb), y, dy, D, w->dHT[cur], m->G(m->lay.rel_emb),
                        m->small_ws.p, st));
+  prof_mark(m, PT_DISTMULT_BWD, st);
   for (int l = m->L - 1; l >= 0; --l) {
     const LayerOffsets& lo = m->lay.layer[l];
     const float* Zl = m->Z + (size_t)l * m->plane();
     IDD_TRY(layer_bwd_pre(p, w->HT[l + 1], w->alpha[l], Zl, D, w->dHT[cur], w->dz, st));
+    prof_mark(m, PT_BWD_PRE, st);
     float* dP = w->dHT[cur];
     // dW_self = [Hin;Tin]ᵀ·dP  (eq. 8), dW_alpha = Hinᵀ·dz, db_alpha = colsum(dz)  (eq. 7)
     IDD_TRY(gemm_tn_splitk_f32(D, D, 2 * T, w->HT[l], D, 0, dP, D, 0, m->G(lo.sk), D, 0, 1, true, m->gemm_ws.p, st));
+    prof_mark(m, PT_DW_SELF, st);
     IDD_TRY(gemm_tn_splitk_f32(D, m->R, T, w->HT[l], D, 0, w->dz, m->R, 0, m->G(lo.wa), m->R, 0, 1, true,
                                m->gemm_ws.p, st));
     IDD_TRY(colsum(w->dz, T, m->R, m->G(lo.ba), 1, m->small_ws.p, st));
+    prof_mark(m, PT_DW_ALPHA, st);
     // dZ_i += scatter(gate_i · dP)  (eq. 10)
     IDD_TRY(segment_scatter(p, dP, w->alpha[l], D, m->dZ + (size_t)l * m->plane(), 1, st));
+    prof_mark(m, PT_SCATTER_DZ, st);
     // d[Hin;Tin] = dP·W_selfᵀ (+ dz·W_alphaᵀ on the head side)  (eq. 9)
     IDD_TRY(transpose_small(m->P(lo.sk), m->wt_ws.p, (int)D, (int)D, 1, st));
     IDD_TRY(gemm_f32(false, false, 2 * T, D, D, dP, D, 0, m->wt_ws.p, D, 0, w->dHT[cur ^ 1], D, 0, 1, false, st));
+    prof_mark(m, PT_DIN, st);
     IDD_TRY(layer_bwd_post(w->dz, m->P(lo.wa), T, D, m->R, w->dHT[cur ^ 1], st));
+    prof_mark(m, PT_BWD_POST, st);
     cur ^= 1;
   }
   // gradient of the two Embedding lookups (eq. 12, second and third term)
   IDD_TRY(segment_scatter(p, w->dHT[cur], nullptr, D, m->G(m->lay.emb), 1, st));
+  prof_mark(m, PT_SCATTER_EMB, st);
   return IDDGCN_OK;
 }
 
@@ -247,10 +287,13 @@ static int node_backward(iddgcn_model* m, const iddgcn_graph* g, const float* va
     float* dZl = m->dZ + (size_t)l * m->plane();
     IDD_TRY(gemm_tn_splitk_f32(D, D, N, m->S, D, N * D, dZl, D, N * D, m->G(lo.rk), D, D * D, m->R, true,
                                m->gemm_ws.p, st));
+    prof_mark(m, PT_DW_REL, st);
     IDD_TRY(transpose_small(m->P(lo.rk), m->wt_ws.p, (int)D, (int)D, m->R, st));
     IDD_TRY(gemm_f32(false, false, N, D, D, dZl, D, N * D, m->wt_ws.p, D, D * D, m->dS, D, N * D, m->R, l > 0, st));
+    prof_mark(m, PT_DS, st);
   }
   IDD_TRY(spmm_bwd_x_range(g, m->dS, D, vals, mode, m->G(m->lay.emb), 1, 0, N, st));
+  prof_mark(m, PT_SPMM_BWD, st);
   if (dvals) IDD_TRY(sddmm_dispatch(g, m->dS, m->P(m->lay.emb), D, vals, mode, dvals, st));
   return IDDGCN_OK;
 }
@@ -261,17 +304,22 @@ static int train_step_body(iddgcn_model* m, const iddgcn_graph* g, const iddgcn_
                            float lr, float b1, float b2, float eps, int64_t step, bool step_on_device,
                            int apply_update, float* loss_out, float* y_out, cudaStream_t st) {
   const int64_t Tt = both->T;
+  m->prof_n = 0;
+  prof_mark(m, PT_START, st);
   IDD_TRY(zero_step_buffers(m, true, st));
+  prof_mark(m, PT_ZERO, st);
   IDD_TRY(node_forward(m, g, nullptr, IDDGCN_VALS_ONES, st));
   IDD_TRY(triple_forward(m, both, w, m->y_all.p, st));                       // IDDGCN.py:147-160
   // y_pred = concat, y_true = [1..1 | 0..0], loss = BCE; loss *= 1/N  (IDDGCN.py:161-168)
   IDD_TRY(bce_loss_grad(m->y_all.p, Tp, Tt, 1.0f / (float)m->N, m->dy_all.p, m->loss_dev, m->small_ws.p, st));
+  prof_mark(m, PT_BCE, st);
   IDD_TRY(triple_backward(m, both, w, m->y_all.p, m->dy_all.p, st));
   IDD_TRY(node_backward(m, g, nullptr, IDDGCN_VALS_ONES, nullptr, st));
   if (apply_update) {
     if (step_on_device) IDD_TRY(increment_counter(m->step_dev, st));
     IDD_TRY(adam_apply(m->params, m->grads, m->adam_m, m->adam_v, m->lay.total, lr, b1, b2, eps, step,
                        step_on_device ? m->step_dev : nullptr, st));          // IDDGCN.py:174
+    prof_mark(m, PT_ADAM, st);
   }
   if (loss_out) IDD_CUDA(cudaMemcpyAsync(loss_out, m->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (y_out) IDD_CUDA(cudaMemcpyAsync(y_out, m->y_all.p, (size_t)Tt * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -420,6 +468,27 @@ int iddgcn_model_release_graph(iddgcn_model_t* m, const iddgcn_graph_t* g) {
   return IDDGCN_OK;
 }
 
+// Per-group timing of iddgcn_model_train_step (not of the captured loop): enable, run a step, read.  ms_by_group has
+// IDDGCN_PROFILE_GROUPS floats (order: ProfTag, see tools/bench_layer.py); reading synchronises the device.
+int iddgcn_model_profile(iddgcn_model_t* m, int enable) {
+  IDD_CHECK(m != nullptr, IDDGCN_EINVAL, "model is NULL");
+  m->prof_on = enable != 0;
+  m->prof_n = 0;
+  return IDDGCN_OK;
+}
+
+int iddgcn_model_profile_read(iddgcn_model_t* m, float* ms_by_group, int n_groups) {
+  IDD_CHECK(m && ms_by_group && n_groups >= (int)PT_COUNT, IDDGCN_EINVAL, "need room for %d groups", (int)PT_COUNT);
+  IDD_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n_groups; ++i) ms_by_group[i] = 0.f;
+  for (size_t i = 1; i < m->prof_n; ++i) {
+    float ms = 0.f;
+    IDD_CUDA(cudaEventElapsedTime(&ms, m->prof_ev[i - 1], m->prof_ev[i]));
+    ms_by_group[m->prof_tag[i]] += ms;
+  }
+  return IDDGCN_OK;
+}
+
 int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p, const float* vals,
                          int vals_mode, float* y, void* stream) {
   IDD_TRY(check_compat(m, g, p));
@@ -499,9 +568,12 @@ int iddgcn_model_train_loop(iddgcn_model_t* m, const iddgcn_graph_t* g, const id
   if (!same) {
     if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
+    const bool prof = m->prof_on;
+    m->prof_on = false;                       // the per-group events belong to the eager step only
     IDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = train_step_body(m, g, both, pos->T, w, lr, beta1, beta2, eps, 0, true, 1, nullptr, nullptr, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    m->prof_on = prof;
     if (rc != IDDGCN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     IDD_CUDA(ce);
     ce = cudaGraphInstantiate(&m->graph_exec, graph, 0);

@@ -84,7 +84,7 @@ def _reduce_scatter(out, inp, index, group):
 
 class GridSpMM:
     def __init__(self, graph, D: int, world: int, rank: int, grid=None, *, exchange: str = "p2p", fwd_fn=None,
-                 bwd_fn=None, device=None, timeout_ms: int = 20000):
+                 bwd_fn=None, device=None, timeout_ms: int = 20000, partials: str = "stores", order: str = "AFB"):
         self.g, self.D, self.world, self.rank = graph, D, world, rank
         self.P_r, self.P_c = parse_grid(grid, world, D)
         self.pr, self.pc = grid_coords(rank, (self.P_r, self.P_c))
@@ -100,6 +100,13 @@ class GridSpMM:
         self.injected = fwd_fn is not None or bwd_fn is not None
         self.exchange = exchange if self.P_r > 1 else "none"
         self.timeout_ms = timeout_ms
+        if partials not in ("stores", "dma") or order not in ("AFB", "ABF"):
+            raise ValueError("partials must be 'stores' or 'dma', order 'AFB' or 'ABF'")
+        # how the partial dX rows of peer-owned nodes travel: "stores" = the backward kernel writes them straight into
+        # the owner's stage buffer (fused, NVLink stores from the SMs); "dma" = the kernel writes them locally and the
+        # copy engines push them while the forward kernel runs.  order: A = peers' node blocks (backward), F = forward,
+        # B = own node block (backward + staged partials).
+        self.partials, self.order = partials, order
         dev = device if device is not None else graph.device
         self.dev = dev
         f = dict(dtype=torch.float32, device=dev)
@@ -147,6 +154,8 @@ class GridSpMM:
         self.h_stage = symm_mem.rendezvous(self.stage, dist.group.WORLD)
         self.h_flags = symm_mem.rendezvous(self.flags, dist.group.WORLD)
         self.timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.part_local = (torch.empty((nslot, self.block, self.Dc), dtype=f32, device=dev)
+                           if self.partials == "dma" else None)
         torch.cuda.synchronize(dev)
         dist.barrier()                              # every rank's flags are zero before anyone signals
         xp, sp, fp = self.h_x.buffer_ptrs, self.h_stage.buffer_ptrs, self.h_flags.buffer_ptrs
@@ -217,10 +226,18 @@ class GridSpMM:
                                                         node_lo, node_hi, arr, len(addends), self._st(stream)))
 
     def _push_partials(self, stream=None):
-        """Backward over the node blocks owned by peers, written straight into their stage buffers (NVLink)."""
+        """Backward over the node blocks owned by peers: written straight into their stage buffers (NVLink stores,
+        partials == "stores") or into a local buffer the copy engines push afterwards (_dma_partials)."""
         for i, q in enumerate(self.peers):
             qlo, qhi, _ = row_block(q, self.P_r, self.N)
-            self._bwd_rows(self.peer_stage_dst[i], qlo, qhi, stream=stream)
+            dst = self.peer_stage_dst[i] if self.part_local is None else self.part_local[i].data_ptr()
+            self._bwd_rows(dst, qlo, qhi, stream=stream)
+
+    def _dma_partials(self, stream):
+        for i, q in enumerate(self.peers):
+            qlo, qhi, _ = row_block(q, self.P_r, self.N)
+            self._lib.check(self.lib.iddgcn_copy_async(self.peer_stage_dst[i], self.part_local[i].data_ptr(),
+                                                       (qhi - qlo) * self.Dc * 4, stream.cuda_stream))
 
     def _own_partial(self, a=0, b=None, stream=None):
         """Backward over (a chunk [a, b) of) this rank's own node block, folding in the staged peer partials."""
@@ -258,14 +275,38 @@ class GridSpMM:
         self._wait(K_DONE, e - 1)                      # peers are done reading what I pushed in the previous step
         ev0 = main.record_event()
         side.wait_event(ev0)
-        self._push_x(side)                             # all-gather leg on the copy engines ...
-        self._signal(K_AG, side)
-        self._push_partials()                          # ... while the backward kernel streams partials to the peers
-        self._signal(K_PART)
-        self._wait(K_AG, e)                            # every peer's X block has landed here
-        self._fwd()
-        self._wait(K_PART, e)                          # every peer's partials for my nodes have landed
-        self._own_partial()
+        if self.order == "AFB":
+            # all-gather leg on the copy engines while the backward kernel produces (and, with partials == "stores",
+            # streams over NVLink) the partials of the peers' node blocks
+            self._push_x(side)
+            self._signal(K_AG, side)
+            self._push_partials()
+            if self.part_local is None:
+                self._signal(K_PART)
+            else:
+                side.wait_event(main.record_event())
+                self._dma_partials(side)               # rides the copy engines while the forward kernel runs
+                self._signal(K_PART, side)
+            self._wait(K_AG, e)                        # every peer's X block has landed here
+            self._fwd()
+            self._wait(K_PART, e)                      # every peer's partials for my nodes have landed
+            self._own_partial()
+        else:
+            # A B F: the partial stores have the links to themselves, then the all-gather push runs under B
+            self._push_partials()
+            if self.part_local is None:
+                self._signal(K_PART)
+                side.wait_event(main.record_event())
+            else:
+                side.wait_event(main.record_event())
+                self._dma_partials(side)
+                self._signal(K_PART, side)
+            self._push_x(side)
+            self._signal(K_AG, side)
+            self._wait(K_PART, e)
+            self._own_partial()
+            self._wait(K_AG, e)
+            self._fwd()
         self._signal(K_DONE)
         main.wait_stream(side)
 
@@ -350,6 +391,14 @@ class GridSpMM:
         cut into node chunks so that dX starts flowing back before the kernel has finished."""
         lib, chk = self.lib, self._lib.check
         main = torch.cuda.current_stream(self.dev)
+        tl = getattr(self, "timeline", None)           # debug: list collecting (label, event) pairs of this step
+
+        def mark(label, stream):
+            if tl is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                tl.append((label, ev))
+
         if not hasattr(self, "s_in"):
             self.s_in = torch.cuda.Stream(device=self.dev)
             self.s_out = torch.cuda.Stream(device=self.dev)
@@ -362,12 +411,15 @@ class GridSpMM:
             e = self.epoch
             self._wait(K_DONE, e - 1, s_in)            # peers no longer read my X block of the previous step
         xv = self.x_local_view()
+        mark("start", s_in)
         chk(lib.iddgcn_copy_async(xv.data_ptr(), Xh.data_ptr(), xv.numel() * 4, s_in.cuda_stream))
+        mark("X up", s_in)
         if p2p:
             self._push_x(s_in)
             self._signal(K_AG, s_in)
         ev_x = s_in.record_event()
         chk(lib.iddgcn_copy_async(self.dS.data_ptr(), dSh.data_ptr(), self.dS.numel() * 4, s_in.cuda_stream))
+        mark("dS up", s_in)
         ev_ds = s_in.record_event()
         main.wait_event(ev_x)
         if p2p:
@@ -380,12 +432,16 @@ class GridSpMM:
         for q in range(chunks):
             lo, hi = total * q // chunks, total * (q + 1) // chunks
             self._fwd(lo, hi)
+            mark(f"fwd chunk {q}", main)
             s_out.wait_event(main.record_event())
             chk(lib.iddgcn_copy_async(Sh.data_ptr() + lo * row_bytes, self.S.data_ptr() + lo * row_bytes,
                                       (hi - lo) * row_bytes, s_out.cuda_stream))
+            mark(f"S down {q}", s_out)
         main.wait_event(ev_ds)
         if p2p:
             self._push_partials()
+            if self.part_local is not None:
+                self._dma_partials(main)
             self._signal(K_PART)
             self._wait(K_PART, e)
         elif self.exchange == "nccl":
@@ -395,9 +451,11 @@ class GridSpMM:
             a, b = self.n_rows * q // chunks, self.n_rows * (q + 1) // chunks
             if self.exchange != "nccl":
                 self._own_partial(a, b)
+            mark(f"bwd chunk {q}", main)
             s_out.wait_event(main.record_event())
             chk(lib.iddgcn_copy_async(dXh.data_ptr() + a * row_bytes, self.dX.data_ptr() + a * row_bytes,
                                       (b - a) * row_bytes, s_out.cuda_stream))
+            mark(f"dX down {q}", s_out)
         if p2p:
             self._signal(K_DONE)
         main.wait_stream(s_out)

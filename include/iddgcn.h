@@ -290,6 +290,11 @@ int iddgcn_model_release_plan(iddgcn_model_t* m, const iddgcn_plan_t* p);
 /* drop the train step captured on graph g (call before destroying g).  The captured step is keyed on unique handle
  * ids and on a workspace generation counter, so a recycled heap address or a regrown workspace never replays it. */
 int iddgcn_model_release_graph(iddgcn_model_t* m, const iddgcn_graph_t* g);
+/* Per-kernel-group timing of ONE iddgcn_model_train_step (measurement aid for the layer-level roofline; the groups are
+ * the phases of IDDGCN.py:123-178 in execution order): enable, run a step, read IDDGCN_PROFILE_GROUPS floats (ms). */
+#define IDDGCN_PROFILE_GROUPS 21
+int iddgcn_model_profile(iddgcn_model_t* m, int enable);
+int iddgcn_model_profile_read(iddgcn_model_t* m, float* ms_by_group, int n_groups);
 /* y [T] = model(head, rel, tail | graph, optional edge vals)   (IDDGCN.py:147-153, IDDGCN_eval.py:97-105) */
 int iddgcn_model_forward(iddgcn_model_t* m, const iddgcn_graph_t* g, const iddgcn_plan_t* p,
                          const float* vals, int vals_mode, float* y, void* stream);

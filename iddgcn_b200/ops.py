@@ -122,7 +122,7 @@ def layer_fwd_dlpack(plan, HT_in, Z, W_self, W_alpha, b_alpha, HT_out, alpha_out
     ts = [HT_in, Z, W_self, W_alpha, b_alpha, HT_out, alpha_out]
     caps = [t.__dlpack__() for t in ts]
     check(load().iddgcn_layer_fwd_dl(plan.handle, *[_dl_ptr(c) for c in caps],
-                                     torch.cuda.current_stream(HT_in.device).cuda_stream))
+                                     torch.cuda.current_stream(plan.device).cuda_stream))
 
 
 def layer_bwd_dlpack(plan, HT_in, HT_out, alpha, Z, W_self, W_alpha, dHT_out, dHT_in, dZ, dW_self, dW_alpha, db_alpha,
@@ -131,7 +131,7 @@ def layer_bwd_dlpack(plan, HT_in, HT_out, alpha, Z, W_self, W_alpha, dHT_out, dH
     a = [t.__dlpack__() for t in (HT_in, HT_out, alpha, Z, W_self, W_alpha, dHT_out, dHT_in, dZ)]
     b = [t.__dlpack__() for t in (dW_self, dW_alpha, db_alpha)]
     check(load().iddgcn_layer_bwd_dl(plan.handle, *[_dl_ptr(c) for c in a], int(accumulate_dZ),
-                                     *[_dl_ptr(c) for c in b], torch.cuda.current_stream(HT_in.device).cuda_stream))
+                                     *[_dl_ptr(c) for c in b], torch.cuda.current_stream(plan.device).cuda_stream))
 
 
 def model_forward_dlpack(model, graph: Graph, plan, y, vals=None, mode: int = VALS_ONES) -> None:

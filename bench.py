@@ -629,13 +629,13 @@ def main():
     ap.add_argument("--no-sddmm", action="store_true", help="skip the separately reported SDDMM line")
     ap.add_argument("--dim", type=int, default=0, help="override the feature width D of the workload (default 128)")
     ap.add_argument("--grid", default="auto", help="rank grid 'RxC': R destination-row blocks x C feature-column "
-                                                    "groups (auto: 1x2, 2x2, 2x4 at 2/4/8 GPUs)")
+                                                    "groups (auto: 1x2, 1x4, 2x4 at 2/4/8 GPUs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="row exchange inside a column group: fused peer-memory kernels or NCCL collectives")
     ap.add_argument("--partials", default="stores", choices=["stores", "dma"],
                     help="p2p exchange: partial dX rows leave through NVLink stores of the backward kernel (fused) or "
                          "through the copy engines")
-    ap.add_argument("--order", default="AFB", choices=["AFB", "ABF"],
+    ap.add_argument("--order", default="ABF", choices=["AFB", "ABF"],
                     help="p2p exchange: kernel order inside a step (A peers' backward blocks, F forward, B own block)")
     ap.add_argument("--check-rows", type=int, default=1_000_000,
                     help="rows (over all ranks) of S and of dX compared with the CPU oracle after the timed region")

@@ -70,6 +70,11 @@ struct iddgcn_plan {
   int32_t* by_tail_ptr = nullptr;   // [N+1]
   int32_t* by_rel_perm = nullptr;   // [T]
   int32_t* by_rel_ptr = nullptr;    // [R+1]
+  // node-major merge of the two orderings: entries by_node_ptr[n]..by_node_ptr[n+1] are the rows of a (2,T,D) buffer
+  // viewed as [2T, D] that node n receives gradient from — its head-side triples (row k) in by-head order, then its
+  // tail-side triples (row T + k) in by-tail order.  One run per node, so the gather backward is a flat stream.
+  int32_t* by_node_ptr = nullptr;   // [N+1]
+  int32_t* by_node_src = nullptr;   // [2T]
 };
 
 namespace iddgcn {

@@ -388,6 +388,26 @@ static int plan_sort_by(const int32_t* field, size_t T, size_t num_bins, int bit
   return IDDGCN_OK;
 }
 
+// merged node-major list (see graph.cuh): one warp per node copies its two runs
+__global__ void plan_node_ptr_kernel(const int32_t* __restrict__ hptr, const int32_t* __restrict__ tptr, size_t N,
+                                     int32_t* __restrict__ nptr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= N) nptr[i] = hptr[i] + tptr[i];
+}
+
+__global__ void plan_node_fill_kernel(const int32_t* __restrict__ hptr, const int32_t* __restrict__ hperm,
+                                      const int32_t* __restrict__ tptr, const int32_t* __restrict__ tperm, size_t N,
+                                      int32_t T, const int32_t* __restrict__ nptr, int32_t* __restrict__ nsrc) {
+  const size_t n = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int hb = hptr[n], he = hptr[n + 1], tb = tptr[n], te = tptr[n + 1];
+  int32_t* dst = nsrc + nptr[n];
+  for (int j = hb + lane; j < he; j += 32) dst[j - hb] = hperm[j];
+  dst += he - hb;
+  for (int j = tb + lane; j < te; j += 32) dst[j - tb] = T + tperm[j];
+}
+
 static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64_t* tail, int64_t T, int on_device,
                             int64_t N, int R, cudaStream_t st, iddgcn_plan* p) {
   IDD_CUDA(cudaGetDevice(&p->device));
@@ -395,18 +415,24 @@ static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64
   const size_t Tz = (size_t)T;
   const size_t Ta = Tz ? Tz : 1;
   {  // one persistent allocation for the nine arrays
-    const size_t bytes = 6 * Arena::pad(Ta * 4) + 2 * Arena::pad(((size_t)N + 1) * 4) + Arena::pad(((size_t)R + 1) * 4);
+    const size_t bytes = 6 * Arena::pad(Ta * 4) + 3 * Arena::pad(((size_t)N + 1) * 4) + Arena::pad(((size_t)R + 1) * 4) +
+                         Arena::pad(2 * Ta * 4);
     IDD_CUDA(pool_alloc(&p->block, bytes));
     Arena a{reinterpret_cast<char*>(p->block), bytes, 0};
     p->head = a.get<int32_t>(Ta); p->rel = a.get<int32_t>(Ta); p->tail = a.get<int32_t>(Ta);
     p->by_head_perm = a.get<int32_t>(Ta); p->by_tail_perm = a.get<int32_t>(Ta); p->by_rel_perm = a.get<int32_t>(Ta);
     p->by_head_ptr = a.get<int32_t>((size_t)N + 1); p->by_tail_ptr = a.get<int32_t>((size_t)N + 1);
     p->by_rel_ptr = a.get<int32_t>((size_t)R + 1);
+    p->by_node_ptr = a.get<int32_t>((size_t)N + 1);
+    p->by_node_src = a.get<int32_t>(2 * Ta);
+    IDD_CHECK(p->by_node_src != nullptr, IDDGCN_ENOMEM, "internal: plan block too small");
   }
+  IDD_CHECK(2 * T < (int64_t)0x7fffff00, IDDGCN_ELIMIT, "plan exceeds the int32 index range (T=%lld)", (long long)T);
   if (!Tz) {
     IDD_CUDA(cudaMemsetAsync(p->by_head_ptr, 0, ((size_t)N + 1) * 4, st));
     IDD_CUDA(cudaMemsetAsync(p->by_tail_ptr, 0, ((size_t)N + 1) * 4, st));
     IDD_CUDA(cudaMemsetAsync(p->by_rel_ptr, 0, ((size_t)R + 1) * 4, st));
+    IDD_CUDA(cudaMemsetAsync(p->by_node_ptr, 0, ((size_t)N + 1) * 4, st));
     IDD_CUDA(cudaStreamSynchronize(st));
     return IDDGCN_OK;
   }
@@ -445,6 +471,13 @@ static int plan_create_impl(const int64_t* head, const int64_t* rel, const int64
                        p->by_tail_ptr));
   IDD_TRY(plan_sort_by(p->rel, Tz, (size_t)R, brr, kA, kB, vA, vB, plan, hist, scratch, st, p->by_rel_perm,
                        p->by_rel_ptr));
+  plan_node_ptr_kernel<<<blocks_for((size_t)N + 1, 256), 256, 0, st>>>(p->by_head_ptr, p->by_tail_ptr, (size_t)N,
+                                                                       p->by_node_ptr);
+  IDD_LAUNCH_CHECK();
+  plan_node_fill_kernel<<<blocks_for((size_t)N * 32, 256), 256, 0, st>>>(p->by_head_ptr, p->by_head_perm, p->by_tail_ptr,
+                                                                         p->by_tail_perm, (size_t)N, (int32_t)T,
+                                                                         p->by_node_ptr, p->by_node_src);
+  IDD_LAUNCH_CHECK();
   int herr = 0;
   IDD_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
   IDD_CUDA(cudaStreamSynchronize(st));  // the arena is freed on return

@@ -5,6 +5,7 @@
 // so the two self-kernel matmuls of a layer are ONE GEMM with M = 2T.  One warp owns one triple; each lane
 // keeps NV float4 slices of the D-wide row (D <= 128*NV).  Gather backward passes are segment sums over
 // the plan's by-head / by-tail orderings: no atomics, fixed summation order.
+#include <stdlib.h>
 #include "triple.cuh"
 
 namespace iddgcn {
@@ -58,7 +59,7 @@ int gather_embeddings(const iddgcn_plan* p, const float* emb, int64_t D, float* 
 
 // ---------------------------------------------------------------------------------------------
 // forward epilogue: gate + gathers of Z_i[head], Z_i[tail] + sigmoid
-template <int NV>
+template <int NV, int RPRE>   // RPRE > 0: rows of up to RPRE relations are prefetched (NV == 1 only)
 __global__ void __launch_bounds__(TW * 32)
     layer_combine_kernel(const int32_t* __restrict__ head, const int32_t* __restrict__ tail,
                          const float4* __restrict__ Hin, const float4* __restrict__ Z,
@@ -71,6 +72,22 @@ __global__ void __launch_bounds__(TW * 32)
   const int lane = threadIdx.x & 31;
   const int64_t k = (int64_t)blockIdx.x * TW + (threadIdx.x >> 5);
   if (k >= T) return;
+  // D <= 128: every row this triple touches (its two pre-activation rows and the 2R gathered Z rows) is requested up
+  // front, so those 2 + 2R independent 512-byte loads are in flight while the gate (a dot product, a warp reduction
+  // and a softmax on the Hin row) is computed; the arithmetic below is unchanged.
+  constexpr bool PRE = RPRE > 0 && NV == 1;
+  float4 pre_p[PRE ? 2 : 1], pre_z[PRE ? 2 : 1][PRE ? RPRE : 1];
+  const int32_t nh0 = head[k], nt0 = tail[k];
+  if (PRE && lane < nvec) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int64_t node = half == 0 ? nh0 : nt0;
+      pre_p[half] = P[((int64_t)half * T + k) * nvec + lane];
+#pragma unroll
+      for (int i = 0; i < (PRE ? RPRE : 1); ++i)
+        if (i < R) pre_z[half][i] = __ldg(Z + ((int64_t)i * N + node) * nvec + lane);
+    }
+  }
   // logits z_i = Hin[k]·W_alpha[:, i] + b_i
   float z[RMAX];
 #pragma unroll
@@ -112,7 +129,20 @@ __global__ void __launch_bounds__(TW * 32)
       if (alpha_out && lane == 0) alpha_out[k * R + i] = a;
       gate[i] = sigmoidf_(a);      // relation_weight (IDDGCN.py:75)
     }
-  const int32_t nh = head[k], nt = tail[k];
+  const int32_t nh = nh0, nt = nt0;
+  if (PRE) {
+    if (lane < nvec) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 acc = pre_p[half];
+#pragma unroll
+        for (int i = 0; i < (PRE ? RPRE : 1); ++i)
+          if (i < R) acc = f4_fma(gate[i], pre_z[half][i], acc);
+        P[((int64_t)half * T + k) * nvec + lane] = f4_sigmoid(acc);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int64_t node = half == 0 ? nh : nt;
@@ -142,9 +172,11 @@ int layer_combine(const iddgcn_plan* p, const float* Hin, const float* Z, const 
   const size_t smem = (size_t)D * p->R * sizeof(float);
 #define IDD_ARGS p->head, p->tail, reinterpret_cast<const float4*>(Hin), reinterpret_cast<const float4*>(Z), W_alpha, \
                  b_alpha, p->T, p->N, nvec, p->R, reinterpret_cast<float4*>(P_inout), alpha_out
-  if (nvec <= 32) layer_combine_kernel<1><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
-  else if (nvec <= 64) layer_combine_kernel<2><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
-  else layer_combine_kernel<4><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  if (nvec <= 32 && p->R <= 2) layer_combine_kernel<1, 2><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else if (nvec <= 32 && p->R <= 4) layer_combine_kernel<1, 4><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else if (nvec <= 32) layer_combine_kernel<1, 0><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else if (nvec <= 64) layer_combine_kernel<2, 0><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
+  else layer_combine_kernel<4, 0><<<grid, TW * 32, smem, st>>>(IDD_ARGS);
 #undef IDD_ARGS
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
@@ -345,10 +377,165 @@ __global__ void __launch_bounds__(TW * 32)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same segment sums in the flat-stream pattern of spmm.cu's stream_rows_kernel, for plans large enough to fill the
+// machine (the warp-per-node kernel above pays three dependent latencies — pointer, permutation, row — for the ~5 rows
+// an average node owns).  A slice of LPR lanes owns a chunk of LPR consecutive nodes; the chunk's run of the plan's
+// merged node-major list (by_node_src: rows of the (2,T,D) buffer viewed as [2T, D]) is staged in shared memory
+// together with the RC gate values of every entry (sigmoid applied once), and consumed in batches of U independent
+// 128-bit row gathers regardless of node boundaries.  Kahan-compensated like the kernel above; the list order is the
+// same (head-side triples, then tail-side), so the two kernels agree to rounding of the compensation terms.
+//   out[(r, n), :] (+)= Σ_{j in ptr[n]..ptr[n+1]} gate_r(src[j] mod T) · dP[src[j], :]     r in [r0, r0+RC)
+constexpr int SEG_SLAB = 256;   // staged entries per warp
+
+template <int LPR, int U, int RC, bool GATED>
+__global__ void __launch_bounds__(TW * 32, 4)
+    segment_stream_kernel(const int32_t* __restrict__ ptr, const int32_t* __restrict__ src,
+                          const float4* __restrict__ dP, const float* __restrict__ alpha, int64_t T, int64_t N, int nvec,
+                          int R, float4* __restrict__ out, int accumulate) {
+  constexpr int SUBS = 32 / LPR;
+  constexpr int SUB_SLAB = SEG_SLAB / SUBS;
+  __shared__ int32_t s_idx[TW][SEG_SLAB];
+  __shared__ float s_w[GATED ? RC : 1][TW][GATED ? SEG_SLAB : 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t chunk = ((int64_t)blockIdx.x * TW + warp) * SUBS + sub;
+  const int64_t n0 = chunk * LPR;
+  if (n0 >= N) return;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int nrows = (N - n0 < LPR) ? (int)(N - n0) : LPR;
+  const int r0 = blockIdx.y * RC;
+  const int planes = GATED ? R : 1;
+  int32_t* const sl_idx = &s_idx[warp][sub * SUB_SLAB];
+
+  const int chunk_beg = ld_stream_i32(ptr + n0);
+  const int my_end = (l < nrows) ? ld_stream_i32(ptr + n0 + l + 1) : 0x7fffffff;
+  const int chunk_end = __shfl_sync(mask, my_end, nrows - 1, LPR);
+  const bool live = l < nvec;
+
+  int row = 0;
+  int cur_end = __shfl_sync(mask, my_end, 0, LPR);
+  int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
+  float4 acc[RC], cmp[RC];
+#pragma unroll
+  for (int i = 0; i < RC; ++i) { acc[i] = f4_zero(); cmp[i] = f4_zero(); }
+
+  auto flush = [&]() {
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        if (r0 + i < planes) {
+          float4* o = out + ((int64_t)(r0 + i) * N + n0 + row) * nvec + l;
+          float4 r = acc[i];
+          if (accumulate) {
+            const float4 pv = *o;
+            r.x += pv.x; r.y += pv.y; r.z += pv.z; r.w += pv.w;
+          }
+          *o = r;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RC; ++i) { acc[i] = f4_zero(); cmp[i] = f4_zero(); }
+    ++row;
+    cur_end = __shfl_sync(mask, my_end, row & (LPR - 1), LPR);
+    if (row >= nrows) cur_end = 0x7fffffff;
+  };
+
+  while (pos < chunk_end) {
+    if (pos + U > slab_hi && slab_hi < chunk_end) {   // refill the slab starting at the current position
+      __syncwarp(mask);
+      slab_lo = pos;
+      slab_hi = (chunk_end - pos < SUB_SLAB) ? chunk_end : pos + SUB_SLAB;
+      for (int q = l; q < slab_hi - slab_lo; q += LPR) {
+        const int s_ = ld_stream_i32(src + slab_lo + q);
+        sl_idx[q] = s_;
+        if (GATED) {
+          const int64_t k = s_ >= T ? s_ - T : s_;
+#pragma unroll
+          for (int i = 0; i < RC; ++i)
+            s_w[i][warp][sub * SUB_SLAB + q] = (r0 + i < R) ? sigmoidf_(__ldg(alpha + k * R + r0 + i)) : 0.f;
+        }
+      }
+      __syncwarp(mask);
+    }
+    const int n = (slab_hi - pos < U) ? (slab_hi - pos) : U;
+    float4 v[U];
+    float w[U][RC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < n) {
+        const int q = pos + u - slab_lo;
+        const int sidx = sl_idx[q];
+        if (GATED) {
+#pragma unroll
+          for (int i = 0; i < RC; ++i) w[u][i] = s_w[i][warp][sub * SUB_SLAB + q];
+        }
+        v[u] = live ? __ldg(dP + (int64_t)sidx * nvec + l) : f4_zero();
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < n) {
+        while (cur_end == pos + u) flush();
+#pragma unroll
+        for (int i = 0; i < RC; ++i) {
+          const float ww = GATED ? w[u][i] : 1.0f;
+          kahan_add(acc[i].x, cmp[i].x, ww * v[u].x);
+          kahan_add(acc[i].y, cmp[i].y, ww * v[u].y);
+          kahan_add(acc[i].z, cmp[i].z, ww * v[u].z);
+          kahan_add(acc[i].w, cmp[i].w, ww * v[u].w);
+        }
+      }
+    }
+    pos += n;
+  }
+  while (row < nrows) flush();
+}
+
+constexpr int64_t SEG_STREAM_MIN_NODES = 65536;
+static bool use_segment_stream(const iddgcn_plan* p, int nvec) {
+  const char* e = getenv("IDDGCN_SEG_STREAM");   // "0" / "1" force the choice (A/B runs and tests)
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1' && nvec <= 32;
+  return p->N >= SEG_STREAM_MIN_NODES && nvec <= 32;
+}
+
+template <int LPR>
+static int launch_segment_stream(const iddgcn_plan* p, const float* dP, const float* alpha, int nvec, float* out,
+                                 int accumulate, cudaStream_t st) {
+  const int64_t blocks = (p->N + TW * 32 - 1) / (TW * 32);   // every warp covers 32 nodes (SUBS chunks of LPR)
+  IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many nodes for one launch");
+  const float4* d4 = reinterpret_cast<const float4*>(dP);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  if (alpha) {
+    if (p->R >= 2) {
+      const dim3 grid((unsigned)blocks, (unsigned)((p->R + 1) / 2));
+      segment_stream_kernel<LPR, 4, 2, true><<<grid, TW * 32, 0, st>>>(p->by_node_ptr, p->by_node_src, d4, alpha, p->T,
+                                                                       p->N, nvec, p->R, o4, accumulate);
+    } else {
+      segment_stream_kernel<LPR, 8, 1, true><<<(unsigned)blocks, TW * 32, 0, st>>>(p->by_node_ptr, p->by_node_src, d4,
+                                                                                   alpha, p->T, p->N, nvec, p->R, o4,
+                                                                                   accumulate);
+    }
+  } else {
+    segment_stream_kernel<LPR, 8, 1, false><<<(unsigned)blocks, TW * 32, 0, st>>>(p->by_node_ptr, p->by_node_src, d4,
+                                                                                  nullptr, p->T, p->N, nvec, p->R, o4,
+                                                                                  accumulate);
+  }
+  IDD_LAUNCH_CHECK();
+  return IDDGCN_OK;
+}
+
 int segment_scatter(const iddgcn_plan* p, const float* dP, const float* alpha, int64_t D, float* out, int accumulate,
                     cudaStream_t st) {
   IDD_CHECK(D % 4 == 0 && D <= 512, IDDGCN_ELIMIT, "unsupported D=%lld", (long long)D);
   const int nvec = (int)(D / 4);
+  if (p->T > 0 && use_segment_stream(p, nvec)) {
+    if (nvec <= 4) return launch_segment_stream<4>(p, dP, alpha, nvec, out, accumulate, st);
+    if (nvec <= 8) return launch_segment_stream<8>(p, dP, alpha, nvec, out, accumulate, st);
+    if (nvec <= 16) return launch_segment_stream<16>(p, dP, alpha, nvec, out, accumulate, st);
+    return launch_segment_stream<32>(p, dP, alpha, nvec, out, accumulate, st);
+  }
   const unsigned gx = (unsigned)((p->N + TW - 1) / TW);
   // few nodes (the shipped graph has 845): one warp per (node, relation) instead of per node
   const bool split_rel = alpha != nullptr && p->N < 32768 && p->R > 1;

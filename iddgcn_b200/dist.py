@@ -37,7 +37,11 @@ import time
 import torch
 import torch.distributed as dist
 
-DEFAULT_GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+# Default grids, from per-rank kernel times measured for every layout on the 20M-node graph (profiles/
+# r02_grid_shapes_*.json) and the 2-GPU runs (profiles/r02_bench_c4_2gpu_*.json): narrow rows gather less efficiently
+# (D/P_c = 128 / 64 / 32 / 16 floats run at 1.03 / 1.00 / 0.86 / 0.5 of the HBM roofline) while every extra row block
+# adds NVLink traffic, so columns are split first and rows only once the rows get too narrow (16 floats).
+DEFAULT_GRIDS = {1: (1, 1), 2: (1, 2), 4: (1, 4), 8: (2, 4)}
 K_DONE, K_AG, K_PART = 0, 1, 2          # flag kinds
 SLOTS = 8                               # flag slots per kind (max ranks in a column group)
 
@@ -84,7 +88,7 @@ def _reduce_scatter(out, inp, index, group):
 
 class GridSpMM:
     def __init__(self, graph, D: int, world: int, rank: int, grid=None, *, exchange: str = "p2p", fwd_fn=None,
-                 bwd_fn=None, device=None, timeout_ms: int = 20000, partials: str = "stores", order: str = "AFB"):
+                 bwd_fn=None, device=None, timeout_ms: int = 20000, partials: str = "stores", order: str = "ABF"):
         self.g, self.D, self.world, self.rank = graph, D, world, rank
         self.P_r, self.P_c = parse_grid(grid, world, D)
         self.pr, self.pc = grid_coords(rank, (self.P_r, self.P_c))
@@ -105,7 +109,9 @@ class GridSpMM:
         # how the partial dX rows of peer-owned nodes travel: "stores" = the backward kernel writes them straight into
         # the owner's stage buffer (fused, NVLink stores from the SMs); "dma" = the kernel writes them locally and the
         # copy engines push them while the forward kernel runs.  order: A = peers' node blocks (backward), F = forward,
-        # B = own node block (backward + staged partials).
+        # B = own node block (backward + staged partials).  Measured on 2 GPUs, 2x1 grid, 20M-node graph (kernels alone
+        # 18.2 ms): stores/ABF 23.7 ms (= the sum of its NVLink-bound phases), dma/AFB 24.1, dma/ABF 27.5, stores/AFB
+        # 28.9 (partial stores and the all-gather push share the links while only A can run), NCCL 34.3.
         self.partials, self.order = partials, order
         dev = device if device is not None else graph.device
         self.dev = dev
@@ -406,18 +412,22 @@ class GridSpMM:
         p2p = self.exchange == "p2p"
         s_in.wait_stream(main)
         s_out.wait_stream(main)
-        if p2p:
-            self.epoch += 1
-            e = self.epoch
-            self._wait(K_DONE, e - 1, s_in)            # peers no longer read my X block of the previous step
         xv = self.x_local_view()
         mark("start", s_in)
         chk(lib.iddgcn_copy_async(xv.data_ptr(), Xh.data_ptr(), xv.numel() * 4, s_in.cuda_stream))
         mark("X up", s_in)
-        if p2p:
-            self._push_x(s_in)
-            self._signal(K_AG, s_in)
         ev_x = s_in.record_event()
+        if p2p:
+            # the NVLink push goes on its own stream: s_in carries nothing but host->device copies and s_out nothing but
+            # device->host copies (with the push queued between the two uploads the downloads were starved while dS
+            # was on its way up: profiles/r02_host_step_timeline_2gpu.json)
+            self.epoch += 1
+            e = self.epoch
+            side = self.s_side
+            side.wait_event(ev_x)
+            self._wait(K_DONE, e - 1, side)            # peers no longer read the X block I pushed in the previous step
+            self._push_x(side)
+            self._signal(K_AG, side)
         chk(lib.iddgcn_copy_async(self.dS.data_ptr(), dSh.data_ptr(), self.dS.numel() * 4, s_in.cuda_stream))
         mark("dS up", s_in)
         ev_ds = s_in.record_event()
@@ -439,6 +449,7 @@ class GridSpMM:
             mark(f"S down {q}", s_out)
         main.wait_event(ev_ds)
         if p2p:
+            self._wait(K_DONE, e - 1)                  # peers are done with the stage buffers of the previous step
             self._push_partials()
             if self.part_local is not None:
                 self._dma_partials(main)
@@ -458,6 +469,7 @@ class GridSpMM:
             mark(f"dX down {q}", s_out)
         if p2p:
             self._signal(K_DONE)
+            main.wait_stream(self.s_side)
         main.wait_stream(s_out)
         main.wait_stream(s_in)
 

@@ -90,7 +90,7 @@ def test_grid_arithmetic():
     assert [row_block(r, 3, 10)[:2] for r in range(3)] == [(0, 4), (4, 8), (8, 10)]
     assert row_block(7, 8, 20_000_000) == (17_500_000, 20_000_000, 2_500_000)
     assert [row_block(r, 4, 5)[:2] for r in range(4)] == [(0, 2), (2, 4), (4, 5), (5, 5)]   # empty trailing block
-    assert parse_grid("auto", 8, 128) == (2, 4) and parse_grid(None, 2, 128) == (1, 2)
+    assert parse_grid("auto", 8, 128) == (2, 4) and parse_grid(None, 2, 128) == (1, 2) and parse_grid(None, 4, 128) == (1, 4)
     assert parse_grid("auto", 8, 8) == (4, 2)          # D=8 cannot be cut into 4 column groups of >= 4 floats
     assert parse_grid("8x1", 8, 128) == (8, 1) and parse_grid((2, 2), 4, 64) == (2, 2)
     with pytest.raises(ValueError):

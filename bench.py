@@ -504,6 +504,9 @@ def run_ours(args, wl):
             # NVLink bound (B200_PROFILING.md: ~770 GB/s per direction per GPU): each rank sends its X block and its
             # partials to P_r-1 peers -> 2 x bytes out, and receives as much
             comm["nvlink_bound_ms"] = 2 * b / 770.0 / 1e6
+        ph = eng.step_phases(iters=5)
+        if ph:
+            comm["phase_done_at_ms_rank0"] = {k: round(v, 3) for k, v in ph.items()}
         fwd_k, bwd_k = float(np.median(kt["fwd"])), float(np.median(kt["bwd"]))
         comm["kernels_ms"] = fwd_k + bwd_k
         comm["step_over_kernels"] = ms_per_step / (fwd_k + bwd_k)

@@ -276,9 +276,19 @@ class GridSpMM:
 
     def _step_p2p(self):
         main, side = torch.cuda.current_stream(self.dev), self.s_side
+        tl = getattr(self, "timeline", None)           # measurement aid: (label, event) pairs of this step
+
+        def mark(label, stream):
+            if tl is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream)
+                tl.append((label, ev))
+
         self.epoch += 1
         e = self.epoch
+        mark("start", main)
         self._wait(K_DONE, e - 1)                      # peers are done reading what I pushed in the previous step
+        mark("peers done with previous step", main)
         ev0 = main.record_event()
         side.wait_event(ev0)
         if self.order == "AFB":
@@ -286,20 +296,28 @@ class GridSpMM:
             # streams over NVLink) the partials of the peers' node blocks
             self._push_x(side)
             self._signal(K_AG, side)
+            mark("X block pushed (side)", side)
             self._push_partials()
+            mark("A: peers' partials", main)
             if self.part_local is None:
                 self._signal(K_PART)
             else:
                 side.wait_event(main.record_event())
                 self._dma_partials(side)               # rides the copy engines while the forward kernel runs
                 self._signal(K_PART, side)
+                mark("partials pushed (side)", side)
             self._wait(K_AG, e)                        # every peer's X block has landed here
+            mark("X blocks arrived", main)
             self._fwd()
+            mark("F: forward", main)
             self._wait(K_PART, e)                      # every peer's partials for my nodes have landed
+            mark("partials arrived", main)
             self._own_partial()
+            mark("B: own block + staged partials", main)
         else:
             # A B F: the partial stores have the links to themselves, then the all-gather push runs under B
             self._push_partials()
+            mark("A: peers' partials", main)
             if self.part_local is None:
                 self._signal(K_PART)
                 side.wait_event(main.record_event())
@@ -307,14 +325,40 @@ class GridSpMM:
                 side.wait_event(main.record_event())
                 self._dma_partials(side)
                 self._signal(K_PART, side)
+                mark("partials pushed (side)", side)
             self._push_x(side)
             self._signal(K_AG, side)
+            mark("X block pushed (side)", side)
             self._wait(K_PART, e)
+            mark("partials arrived", main)
             self._own_partial()
+            mark("B: own block + staged partials", main)
             self._wait(K_AG, e)
+            mark("X blocks arrived", main)
             self._fwd()
+            mark("F: forward", main)
         self._signal(K_DONE)
         main.wait_stream(side)
+        mark("end", main)
+
+    def step_phases(self, iters=5):
+        """Median completion time (ms since the step start, this rank) of every phase of the p2p step."""
+        if self.exchange != "p2p":
+            return None
+        acc = {}
+        for _ in range(iters):
+            self.timeline = []
+            self.step()
+            torch.cuda.synchronize(self.dev)
+            t0 = self.timeline[0][1]
+            for label, ev in self.timeline[1:]:
+                acc.setdefault(label, []).append(t0.elapsed_time(ev))
+        self.timeline = None
+        out = {}
+        for k, v in acc.items():
+            v.sort()
+            out[k] = v[len(v) // 2]
+        return out
 
     def _step_nccl(self):
         grp = self.col_group

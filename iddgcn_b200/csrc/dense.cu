@@ -186,19 +186,35 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
   for (int c = 0; c < NV; ++c)
 #pragma unroll
     for (int n = 0; n < SK_NMAX; ++n) acc[c][n][0] = acc[c][n][1] = acc[c][n][2] = acc[c][n][3] = 0.f;
-  for (int64_t r = r0 + warp; r < r1; r += SK_WARPS) {
-    float b[SK_NMAX];
+  // SK_UNROLL rows of this warp are requested before any is consumed (one 512-byte row per iteration left the warp
+  // with a single load in flight); rows are still accumulated in the same order, so results are bit-identical
+  constexpr int SK_UNROLL = NV == 1 ? 4 : 2;
+  for (int64_t rb = r0 + warp; rb < r1; rb += (int64_t)SK_WARPS * SK_UNROLL) {
+    float b[SK_UNROLL][SK_NMAX];
+    float4 a[SK_UNROLL][NV];
 #pragma unroll
-    for (int n = 0; n < SK_NMAX; ++n) b[n] = n < N ? __ldg(B + r * ldb + n) : 0.f;
+    for (int u = 0; u < SK_UNROLL; ++u) {
+      const int64_t r = rb + (int64_t)u * SK_WARPS;
 #pragma unroll
-    for (int c = 0; c < NV; ++c) {
-      const int v = lane + c * 32;
-      if (v < nvec) {
-        const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(A + r * lda) + v);
+      for (int n = 0; n < SK_NMAX; ++n) b[u][n] = (r < r1 && n < N) ? __ldg(B + r * ldb + n) : 0.f;
 #pragma unroll
-        for (int n = 0; n < SK_NMAX; ++n) {
-          acc[c][n][0] += a.x * b[n]; acc[c][n][1] += a.y * b[n];
-          acc[c][n][2] += a.z * b[n]; acc[c][n][3] += a.w * b[n];
+      for (int c = 0; c < NV; ++c) {
+        const int v = lane + c * 32;
+        a[u][c] = (r < r1 && v < nvec) ? ld_stream_f4(reinterpret_cast<const float4*>(A + r * lda) + v)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SK_UNROLL; ++u) {
+      if (rb + (int64_t)u * SK_WARPS >= r1) break;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        if (lane + c * 32 < nvec) {
+#pragma unroll
+          for (int n = 0; n < SK_NMAX; ++n) {
+            acc[c][n][0] += a[u][c].x * b[u][n]; acc[c][n][1] += a[u][c].y * b[u][n];
+            acc[c][n][2] += a[u][c].z * b[u][n]; acc[c][n][3] += a[u][c].w * b[u][n];
+          }
         }
       }
     }

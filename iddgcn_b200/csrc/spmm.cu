@@ -44,6 +44,13 @@ __device__ __forceinline__ void add_rows(float4& r, const AddSrcs& add, size_t v
   }
 }
 
+// Σ_j add.p[j][vec_index] in the order given (zero when there is none) — the value the epilogue adds to a row
+__device__ __forceinline__ float4 addend_sum(const AddSrcs& add, size_t vec_index) {
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  add_rows(t, add, vec_index);
+  return t;
+}
+
 template <int MODE>
 __device__ __forceinline__ float edge_weight(const float* __restrict__ vals, int e) {
   if (MODE == IDDGCN_VALS_ONES) return 1.0f;
@@ -130,7 +137,8 @@ __global__ void __launch_bounds__(SPMM_THREADS)
     const int vi = l + c * LPR;
     if (vi < nvec) {
       float4 r = acc[c];
-      add_rows(r, add, (size_t)o * nvec + vi);
+      const float4 t = addend_sum(add, (size_t)o * nvec + vi);
+      r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
       st_stream_f4(orow + vi, r);
     }
   }
@@ -186,12 +194,25 @@ __global__ void __launch_bounds__(TPB, MINB)
     int cur_end = __shfl_sync(mask, my_end, 0, LPR);
     int pos = chunk_beg, slab_lo = chunk_beg, slab_hi = chunk_beg;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The addends of a row (staged peer partials) are requested two rows ahead: loaded inside the flush they were a
+    // dependent ~1 us load at every row end (the own-block launch of the partitioned backward ran at half speed).
+    float4 pre_a = make_float4(0.f, 0.f, 0.f, 0.f), pre_b = pre_a;
+    if constexpr (ADD) {
+      if (l < nvec) {
+        pre_a = addend_sum(add, (size_t)r0 * nvec + l);
+        if (nrows > 1) pre_b = addend_sum(add, (size_t)(r0 + 1) * nvec + l);
+      }
+    }
 
     auto flush = [&]() {
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        if constexpr (ADD) add_rows(r, add, (size_t)(r0 + row) * nvec + l);
+        if constexpr (ADD) {
+          r.x += pre_a.x; r.y += pre_a.y; r.z += pre_a.z; r.w += pre_a.w;
+          pre_a = pre_b;
+          if (row + 2 < nrows) pre_b = addend_sum(add, (size_t)(r0 + row + 2) * nvec + l);
+        }
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,7 +271,10 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        if constexpr (ADD) add_rows(r, add, (size_t)(r0 + row) * nvec + l);
+        if constexpr (ADD) {
+          const float4 t = addend_sum(add, (size_t)(r0 + row) * nvec + l);
+          r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+        }
         st_stream_f4(o, r);
       }
       acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -416,7 +440,8 @@ __global__ void __launch_bounds__(256)
       const float4 p = s4[(size_t)sg * nvec + vi];
       acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
     }
-    add_rows(acc, add, (size_t)row * nvec + vi);
+    const float4 t = addend_sum(add, (size_t)row * nvec + vi);   // same association as the row kernels: acc + (Σ_j a_j)
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     o4[vi] = acc;
   }
 }
@@ -786,12 +811,13 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
   // the epilogue addends (accumulate / staged peer partials) exist only on the backward side (USE_PERM) and are a
-  // separate instantiation, so the plain kernels keep the register allocation they were tuned with (64, no spills)
+  // separate instantiation (3 blocks per SM: the prefetched addends need ~70 registers), so the plain kernels keep the
+  // register allocation they were tuned with (64 registers, 4 blocks, no spills)
 #define IDD_STREAM_ARGS a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t
 #define IDD_STREAM2(MODE_, HUBS_)                                                                                    \
   do {                                                                                                               \
     if (USE_PERM && a.add.n > 0)                                                                                     \
-      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_, SPMM_THREADS, 4, false, USE_PERM>                           \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_, SPMM_THREADS, 3, false, USE_PERM>                           \
           <<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS);                                              \
     else                                                                                                             \
       stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS); \

@@ -262,6 +262,19 @@ __global__ void __launch_bounds__(256) layer_bwd_post_kernel(const float* __rest
   const int d = (int)(i - k * nvec) * 4;
   float4* p = reinterpret_cast<float4*>(dHin) + i;
   float4 acc = *p;
+  if (R == 2) {
+    // the 4 x R weights of this float4 are contiguous in W_alpha [D][R]: two 128-bit loads instead of eight scalar
+    // ones; same products, same order (r = 0 then r = 1 per element)
+    const float2 z = *reinterpret_cast<const float2*>(dz + k * 2);
+    const float4 w01 = __ldg(reinterpret_cast<const float4*>(W_alpha + (size_t)d * 2));
+    const float4 w23 = __ldg(reinterpret_cast<const float4*>(W_alpha + (size_t)d * 2) + 1);
+    acc.x = fmaf(z.y, w01.y, fmaf(z.x, w01.x, acc.x));
+    acc.y = fmaf(z.y, w01.w, fmaf(z.x, w01.z, acc.y));
+    acc.z = fmaf(z.y, w23.y, fmaf(z.x, w23.x, acc.z));
+    acc.w = fmaf(z.y, w23.w, fmaf(z.x, w23.z, acc.w));
+    *p = acc;
+    return;
+  }
   for (int r = 0; r < R; ++r) {
     const float z = dz[k * R + r];
     acc.x = fmaf(z, __ldg(W_alpha + (d + 0) * R + r), acc.x);

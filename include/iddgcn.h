@@ -140,8 +140,8 @@ int iddgcn_edge_value_sums(const iddgcn_graph_t* g, const float* vals, int vals_
  *                            may be memory of a PEER GPU mapped into this process (NVLink peer stores: the partial
  *                            rows land in the owner's stage buffer as they are produced — a fused reduce-scatter).
  *                            addends[0..n_addends) (<= 8, host array of device pointers, each at the first row of the
- *                            range) are added to the gathered sum in the epilogue in the order given:
- *                            dX_rows[k] = Σ_r A_rᵀ dS_r [k] + Σ_j addends[j][k]   (how the owner folds the partials its
+ *                            range) are summed in the order given and added to the gathered sum in the epilogue:
+ *                            dX_rows[k] = Σ_r A_rᵀ dS_r [k] + (Σ_j addends[j][k])   (how the owner folds the partials its
  *                            peers pushed; n_addends=1 with addends[0]==dX_rows is the classic "accumulate").
  *   iddgcn_spmm_prepare    : size the hub-row workspace for feature width D now (needed before a stream capture). */
 int iddgcn_spmm_fwd_rows(const iddgcn_graph_t* g, const float* X, int64_t D, const float* vals, int vals_mode,

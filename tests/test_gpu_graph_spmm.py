@@ -344,7 +344,7 @@ def test_row_ranges_addends_and_hub_rows_v2(D, monkeypatch):
     out = torch.full((N, D), -7.0, device="cuda")
     for lo, hi in [(0, 18), (18, 3000), (3000, N)]:
         ops.spmm_bwd_x_rows(g, dSd, out[lo:], lo, hi, addends=[a1[lo:], a2[lo:]])
-    assert torch.equal(out, (dX_full + a1) + a2)
+    assert torch.equal(out, dX_full + (a1 + a2))        # addends are summed in order, then added to the gathered sum
     plain = torch.empty((N, D), device="cuda")
     ops.spmm_bwd_x_rows(g, dSd, plain, 0, N)
     assert torch.equal(plain, dX_full)

@@ -46,6 +46,11 @@ __device__ __forceinline__ void add_rows(float4& r, const AddSrcs& add, size_t v
 
 // Σ_j add.p[j][vec_index] in the order given (zero when there is none) — the value the epilogue adds to a row
 __device__ __forceinline__ float4 addend_sum(const AddSrcs& add, size_t vec_index) {
+  // One addend (two row blocks, or `accumulate`) is the common case and gets a single unconditional load: in the
+  // general predicated chain below every `t += load_j` reuses the same registers, so the instruction after the first
+  // load waits for it even when j >= n — which turned the prefetch back into a dependent load (3.05 ms instead of 1.4 ms
+  // for the own-block launch, profiles/r02_addend_epilogue_microbench.json).
+  if (add.n == 1) return *(reinterpret_cast<const float4*>(add.p[0]) + vec_index);
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
   add_rows(t, add, vec_index);
   return t;
@@ -810,13 +815,18 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   constexpr int rows_per_block = (SPMM_THREADS / 32) * 32;  // every warp covers 32 rows (SUBS chunks of LPR)
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
+  const char* am = getenv("IDDGCN_ADD_MINB");   // A/B: blocks per SM of the addend instantiation (3 default, 4)
+  const int add_minb = (am && am[0] == '4') ? 4 : 3;
   // the epilogue addends (accumulate / staged peer partials) exist only on the backward side (USE_PERM) and are a
   // separate instantiation (3 blocks per SM: the prefetched addends need ~70 registers), so the plain kernels keep the
   // register allocation they were tuned with (64 registers, 4 blocks, no spills)
 #define IDD_STREAM_ARGS a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t
 #define IDD_STREAM2(MODE_, HUBS_)                                                                                    \
   do {                                                                                                               \
-    if (USE_PERM && a.add.n > 0)                                                                                     \
+    if (USE_PERM && a.add.n > 0 && add_minb == 4)                                                                    \
+      stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_, SPMM_THREADS, 4, false, USE_PERM>                           \
+          <<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS);                                              \
+    else if (USE_PERM && a.add.n > 0)                                                                                \
       stream_rows_kernel<LPR, 8, MODE_, USE_PERM, HUBS_, SPMM_THREADS, 3, false, USE_PERM>                           \
           <<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(IDD_STREAM_ARGS);                                              \
     else                                                                                                             \

@@ -173,8 +173,15 @@ __global__ void __launch_bounds__(TPB, MINB)
   constexpr int SUBS = 32 / LPR;
   constexpr int SUB_SLAB = SLAB / SUBS;
   constexpr bool WEIGHTED = MODE != IDDGCN_VALS_ONES;
+  // Narrow rows (D <= 32) with epilogue addends: the addend rows of the slice's LPR output rows are contiguous, so the
+  // slice stages their sum in shared memory once per chunk (LPR x LPR float4, coalesced) and the flush adds from there.
+  // With 4 or 8 slices per warp flushing at different moments a per-flush global load — even one requested two rows
+  // ahead — made the own-block launch of the partitioned backward 1.9x slower than the same launch without addends
+  // (profiles/r02_addend_epilogue_microbench.json); wide rows (one or two slices per warp) keep the register prefetch.
+  constexpr bool ADD_SMEM = ADD && LPR <= 8 && !WEIGHTED && !HUBS;
   __shared__ int32_t s_idx[TPB / 32][SLAB];
   __shared__ float s_w[WEIGHTED ? TPB / 32 : 1][WEIGHTED ? SLAB : 1];
+  __shared__ float4 s_add[ADD_SMEM ? TPB / 32 : 1][ADD_SMEM ? 32 * LPR : 1];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR;
@@ -202,7 +209,12 @@ __global__ void __launch_bounds__(TPB, MINB)
     // The addends of a row (staged peer partials) are requested two rows ahead: loaded inside the flush they were a
     // dependent ~1 us load at every row end (the own-block launch of the partitioned backward ran at half speed).
     float4 pre_a = make_float4(0.f, 0.f, 0.f, 0.f), pre_b = pre_a;
-    if constexpr (ADD) {
+    float4* const sl_add = ADD_SMEM ? &s_add[warp][sub * LPR * LPR] : nullptr;
+    if constexpr (ADD_SMEM) {
+      const int total = nrows * nvec;                        // the chunk's addend rows are one contiguous range
+      for (int i = l; i < total; i += LPR) sl_add[i] = addend_sum(add, (size_t)r0 * nvec + i);
+      __syncwarp(mask);
+    } else if constexpr (ADD) {
       if (l < nvec) {
         pre_a = addend_sum(add, (size_t)r0 * nvec + l);
         if (nrows > 1) pre_b = addend_sum(add, (size_t)(r0 + 1) * nvec + l);
@@ -213,7 +225,10 @@ __global__ void __launch_bounds__(TPB, MINB)
       if (l < nvec) {
         float4 r = acc;
         float4* o = out4 + (size_t)row * nvec + l;
-        if constexpr (ADD) {
+        if constexpr (ADD_SMEM) {
+          const float4 t = sl_add[row * nvec + l];
+          r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+        } else if constexpr (ADD) {
           r.x += pre_a.x; r.y += pre_a.y; r.z += pre_a.z; r.w += pre_a.w;
           pre_a = pre_b;
           if (row + 2 < nrows) pre_b = addend_sum(add, (size_t)(r0 + row + 2) * nvec + l);
@@ -815,8 +830,11 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
   constexpr int rows_per_block = (SPMM_THREADS / 32) * 32;  // every warp covers 32 rows (SUBS chunks of LPR)
   const int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
   IDD_CHECK(blocks < (int64_t)0x7fffffff, IDDGCN_ELIMIT, "too many rows for one launch");
-  const char* am = getenv("IDDGCN_ADD_MINB");   // A/B: blocks per SM of the addend instantiation (3 default, 4)
-  const int add_minb = (am && am[0] == '4') ? 4 : 3;
+  // blocks per SM of the addend instantiation: the shared-memory variant (narrow rows, see the kernel) needs no extra
+  // registers and keeps 4; the register-prefetch variant needs ~70 registers -> 3.  IDDGCN_ADD_MINB=3/4 forces (A/B).
+  const char* am = getenv("IDDGCN_ADD_MINB");
+  const bool smem_variant = LPR <= 8 && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff;
+  const int add_minb = (am && (am[0] == '3' || am[0] == '4')) ? (am[0] - '0') : (smem_variant ? 4 : 3);
   // the epilogue addends (accumulate / staged peer partials) exist only on the backward side (USE_PERM) and are a
   // separate instantiation (3 blocks per SM: the prefetched addends need ~70 registers), so the plain kernels keep the
   // register allocation they were tuned with (64 registers, 4 blocks, no spills)

@@ -370,3 +370,31 @@ def test_empty_row_block_graph():
     assert g.n_rows == 0 and g.nnz == 0
     dX = ops.spmm_bwd_x(g, torch.zeros((2, 0, 8), device="cuda"))
     assert dX.shape == (50, 8) and float(dX.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("D", [8, 16, 24, 32, 64, 128])
+def test_addends_without_hub_rows_all_widths(D, monkeypatch):
+    """Epilogue addends on a graph WITHOUT hub rows (the instantiation the partitioned backward runs at bench scale):
+    narrow rows stage the addend rows in shared memory, wide rows prefetch them in registers; one, two and in-place
+    addends, odd row ranges, must equal the plain result plus the addends bit for bit."""
+    monkeypatch.setenv("IDDGCN_SPMM_V1", "0")
+    from iddgcn_b200 import ops
+    from iddgcn_b200.graph import Graph
+    N, R = 70001, 2
+    rng = np.random.default_rng(D)
+    tri = np.stack([rng.integers(0, N, 400000), rng.integers(0, R, 400000), rng.integers(0, N, 400000)], 1).astype(np.int64)
+    tri = tri[(tri[:, 2] % 11) != 4]                 # nodes without in-edges: rows that are pure addend
+    g = Graph(tri, N, R)
+    dS = torch.from_numpy(rng.standard_normal((R, N, D)).astype(np.float32)).cuda()
+    a1 = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).cuda()
+    a2 = torch.from_numpy(rng.standard_normal((N, D)).astype(np.float32)).cuda()
+    plain = ops.spmm_bwd_x(g, dS)
+    for lo, hi in [(0, N), (5, 40003), (40003, N)]:
+        out = torch.full((N, D), -7.0, device="cuda")
+        ops.spmm_bwd_x_rows(g, dS, out[lo:], lo, hi, addends=[a1[lo:]])
+        assert torch.equal(out[lo:hi], plain[lo:hi] + a1[lo:hi]) and float(out[:lo].max(initial=-7.0)) == -7.0
+        ops.spmm_bwd_x_rows(g, dS, out[lo:], lo, hi, addends=[a1[lo:], a2[lo:]])
+        assert torch.equal(out[lo:hi], plain[lo:hi] + (a1[lo:hi] + a2[lo:hi]))
+        acc = a2.clone()
+        ops.spmm_bwd_x_rows(g, dS, acc[lo:], lo, hi, addends=[acc[lo:]])
+        assert torch.equal(acc[lo:hi], plain[lo:hi] + a2[lo:hi])

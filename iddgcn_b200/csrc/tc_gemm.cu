@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
+#include <stdlib.h>
 #include "dense.cuh"
 
 namespace iddgcn {
@@ -155,6 +156,10 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(u);
 }
 
+__device__ __forceinline__ float tf32_trunc(float x) {   // the 19 bits a kind::tf32 operand is read with
+  return __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
+
 // in: [batch][rows][cols] row-major.  transpose == 0: hi/lo are [batch][rows][cols]; else [batch][cols][rows].
 __global__ void split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo,
                                   int rows, int cols, int64_t in_stride, int transpose) {
@@ -186,7 +191,7 @@ template <int N_, int K_, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                       const __grid_constant__ CUtensorMap map_blo, float* __restrict__ C, int64_t ldc, int64_t M,
-                      int accumulate) {
+                      int accumulate, int hw_trunc) {
   using L = TcSmem<N_, K_, STAGES>;
   constexpr int KBLOCKS = L::KBLOCKS;
   constexpr int TMEM_COLS = 2 * N_;
@@ -326,14 +331,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(bar_full(s), ph);
         float4* hi = reinterpret_cast<float4*>(base_ptr + L::B_BYTES + (size_t)s * 2 * TC_A_SLAB);
         float4* lo = hi + TC_A_SLAB / 16;
+        if (hw_trunc) {
+          // A_hi is what the tensor core reads from the raw fp32 block anyway (kind::tf32 ignores the low 13 mantissa
+          // bits): leave the landed block untouched and write only A_lo = A - trunc(A) — half the splitter's stores
 #pragma unroll
-        for (int i = 0; i < TC_A_SLAB / 16 / 128; ++i) {
-          const int o = i * 128 + t;
-          const float4 x = hi[o];
-          const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
-          hi[o] = h;
-          lo[o] = make_float4(tf32_round(x.x - h.x), tf32_round(x.y - h.y), tf32_round(x.z - h.z),
-                              tf32_round(x.w - h.w));
+          for (int i = 0; i < TC_A_SLAB / 16 / 128; ++i) {
+            const int o = i * 128 + t;
+            const float4 x = hi[o];
+            lo[o] = make_float4(tf32_round(x.x - tf32_trunc(x.x)), tf32_round(x.y - tf32_trunc(x.y)),
+                                tf32_round(x.z - tf32_trunc(x.z)), tf32_round(x.w - tf32_trunc(x.w)));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < TC_A_SLAB / 16 / 128; ++i) {
+            const int o = i * 128 + t;
+            const float4 x = hi[o];
+            const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+            hi[o] = h;
+            lo[o] = make_float4(tf32_round(x.x - h.x), tf32_round(x.y - h.y), tf32_round(x.z - h.z),
+                                tf32_round(x.w - h.w));
+          }
         }
         fence_proxy_async();                                   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(bar_ready(s));
@@ -409,7 +426,10 @@ int launch_tc(const float* A, int64_t lda, const float* Bhi, const float* Blo, f
   IDD_TRY(make_map(&ml, Blo, N_, K_, K_, N_));
   const int64_t tiles = (M + TC_BLOCK_M - 1) / TC_BLOCK_M;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(ma, mh, ml, C, ldc, M, accumulate);
+  // A_hi from the tensor core's own truncation (default; IDDGCN_TC_AHI_TRUNC=0 restores the rounded in-place split):
+  // 2.18 -> 2.10 ms at D=128, 1.08 -> 0.94 ms at D=64 for 9.4 M rows (profiles/r02_dense_transform_hw_trunc_ab.json)
+  const char* ht = getenv("IDDGCN_TC_AHI_TRUNC");
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(ma, mh, ml, C, ldc, M, accumulate, (ht && ht[0] == '0') ? 0 : 1);
   IDD_LAUNCH_CHECK();
   return IDDGCN_OK;
 }

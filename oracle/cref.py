@@ -62,6 +62,18 @@ def spmm_csr(ptr, idx, val, X, out=None, threads=0):
     return out
 
 
+def spmm_csr_acc64(ptr, idx, val, X, out=None, threads=0):
+    """spmm_csr with double accumulators (rounded to float32 at the end) — the accuracy reference for hub rows."""
+    D = X.shape[1]
+    assert D <= 1024
+    nseg = len(ptr) - 1
+    if out is None:
+        out = np.empty((nseg, D), np.float32)
+    load().spmm_csr_omp_acc64(_p(ptr), _p(idx), _p(val), C.c_int64(nseg), _p(X), C.c_int64(D), _p(out),
+                              C.c_int(threads))
+    return out
+
+
 def spmm_csc_bwd(cscptr, cscrow, perm, val, R, N, n_rows, dS, out=None, threads=0):
     D = dS.shape[-1]
     if out is None:

@@ -79,3 +79,25 @@ void spmm_csc_bwd_omp(const int32_t* cscptr, const int32_t* cscrow, const int32_
     }
   }
 }
+
+/* Same product with a double accumulator per output element, rounded to float once at the end: the accuracy reference
+ * for rows of very high degree (a sequential fp32 sum of 10^6 terms is itself ~1e-5 off), used next to spmm_csr_omp by
+ * bench.py's parity check.  D <= 1024. */
+void spmm_csr_omp_acc64(const int32_t* ptr, const int32_t* idx, const float* val, int64_t num_segs, const float* b,
+                        int64_t D, float* out, int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t s = 0; s < num_segs; ++s) {
+    double acc[1024];
+    for (int64_t d = 0; d < D; ++d) acc[d] = 0.0;
+    for (int32_t e = ptr[s]; e < ptr[s + 1]; ++e) {
+      const double v = val ? (double)val[e] : 1.0;
+      const float* src = b + (int64_t)idx[e] * D;
+      for (int64_t d = 0; d < D; ++d) acc[d] += v * (double)src[d];
+    }
+    float* dst = out + s * D;
+    for (int64_t d = 0; d < D; ++d) dst[d] = (float)acc[d];
+  }
+}

@@ -39,6 +39,7 @@ def test_our_arm_line_on_small_workload():
     assert BASE_KEYS | {"roofline", "clocks", "sddmm", "parity_check"} <= set(d)
     pc = d["parity_check"]
     assert pc["ok"] is True and pc["rows"] == 100_000 and pc["max_rel_err"] <= 1e-5 and pc["edges"] > 1_000_000
+    assert pc["vs_tf_cpu_order_fp32"] == 0.0          # uniform graph, one GPU: bit-equal to TF-CPU's summation order
     assert d["value"] > 1e8 and d["n_gpus"] == 1 and d["steps"] == 3 and d["gpu_launches"] >= 6
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9

@@ -170,6 +170,9 @@ def test_c_restatement_matches_numpy_oracle():
     assert rel_err(S2, O.spmm_fwd(adj, X.astype(np.float64), vals)) < 1e-6
     dX2 = cref.spmm_csc_bwd(st["csc_rowptr"], st["csc_row"], st["csc_perm"], v, R, N, N, dS)
     assert rel_err(dX2, O.spmm_bwd_x(adj, dS.astype(np.float64), vals)) < 1e-6
+    # double-accumulator flavour (bench.py's accuracy reference for hub rows): the fp64 oracle rounded once to float32
+    S64 = cref.spmm_csr_acc64(st["csr_rowptr"], st["csr_col"], v, X).reshape(R, N, D)
+    assert np.array_equal(S64, O.spmm_fwd(adj, X.astype(np.float64), vals).astype(np.float32))
 
 
 def test_train_step_descends():

@@ -305,8 +305,9 @@ def parity_check(torch, eng, raw, N_total, R, D, n_sample, seed):
     Dc, col_lo, lo, n_rows = eng.Dc, eng.pc * eng.Dc, eng.lo, eng.n_rows
     rng = np.random.default_rng(seed)
     m = min(n_sample, n_rows)
-    if m <= 0:
-        return {"rows": 0, "max_abs_err": 0.0, "max_rel_err": 0.0, "edges": 0}
+    if m <= 0:                                          # a rank that owns no rows (empty trailing block)
+        return {"rows": 0, "edges": 0, "max_abs_err": 0.0, "max_rel_err": 0.0, "fwd_rel_err": 0.0, "bwd_rel_err": 0.0,
+                "vs_tf_cpu_order_fp32": 0.0, "max_row_degree": 0}
     picked = np.sort(rng.choice(n_rows, m, replace=False)) if m < n_rows else np.arange(n_rows)
     gid = picked + lo                                   # global ids: destination rows for S, source nodes for dX
     lut = np.full(N_total, -1, np.int32)

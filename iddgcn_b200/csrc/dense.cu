@@ -172,7 +172,7 @@ int gemm_f32_simt(bool transA, bool transB, int64_t M, int64_t N, int64_t K, con
 constexpr int SK_WARPS = 8;
 constexpr int SK_NMAX = 8;
 
-template <int NV>
+template <int NV, int NMAX = SK_NMAX>   // NMAX: columns of B kept in registers (>= N); 2 for the gate gradient at R = 2
 __global__ void __launch_bounds__(SK_WARPS * 32)
     tn_skinny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb, int64_t K, int M,
                      int N, int64_t rows_per_block, float* __restrict__ ws) {
@@ -181,22 +181,22 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
   const int nvec = M >> 2;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = r0 + rows_per_block < K ? r0 + rows_per_block : K;
-  float acc[NV][SK_NMAX][4];
+  float acc[NV][NMAX][4];
 #pragma unroll
   for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int n = 0; n < SK_NMAX; ++n) acc[c][n][0] = acc[c][n][1] = acc[c][n][2] = acc[c][n][3] = 0.f;
+    for (int n = 0; n < NMAX; ++n) acc[c][n][0] = acc[c][n][1] = acc[c][n][2] = acc[c][n][3] = 0.f;
   // SK_UNROLL rows of this warp are requested before any is consumed (one 512-byte row per iteration left the warp
   // with a single load in flight); rows are still accumulated in the same order, so results are bit-identical
-  constexpr int SK_UNROLL = NV == 1 ? 4 : 2;
+  constexpr int SK_UNROLL = NV == 1 ? (NMAX <= 2 ? 8 : 4) : 2;   // rows in flight per warp
   for (int64_t rb = r0 + warp; rb < r1; rb += (int64_t)SK_WARPS * SK_UNROLL) {
-    float b[SK_UNROLL][SK_NMAX];
+    float b[SK_UNROLL][NMAX];
     float4 a[SK_UNROLL][NV];
 #pragma unroll
     for (int u = 0; u < SK_UNROLL; ++u) {
       const int64_t r = rb + (int64_t)u * SK_WARPS;
 #pragma unroll
-      for (int n = 0; n < SK_NMAX; ++n) b[u][n] = (r < r1 && n < N) ? __ldg(B + r * ldb + n) : 0.f;
+      for (int n = 0; n < NMAX; ++n) b[u][n] = (r < r1 && n < N) ? __ldg(B + r * ldb + n) : 0.f;
 #pragma unroll
       for (int c = 0; c < NV; ++c) {
         const int v = lane + c * 32;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
       for (int c = 0; c < NV; ++c) {
         if (lane + c * 32 < nvec) {
 #pragma unroll
-          for (int n = 0; n < SK_NMAX; ++n) {
+          for (int n = 0; n < NMAX; ++n) {
             acc[c][n][0] += a[u][c].x * b[u][n]; acc[c][n][1] += a[u][c].y * b[u][n];
             acc[c][n][2] += a[u][c].z * b[u][n]; acc[c][n][3] += a[u][c].w * b[u][n];
           }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
     const int v = lane + c * 32;
     if (v < nvec)
 #pragma unroll
-      for (int n = 0; n < SK_NMAX; ++n)
+      for (int n = 0; n < NMAX; ++n)
         if (n < N)
 #pragma unroll
           for (int e = 0; e < 4; ++e) sk_smem[((size_t)warp * M + v * 4 + e) * N + n] = acc[c][n][e];
@@ -291,7 +291,8 @@ int gemm_tn_splitk_f32(int64_t M, int64_t N, int64_t K, const float* A, int64_t 
       const float* Ab = A + (int64_t)b * strideA;
       const float* Bb = B + (int64_t)b * strideB;
       float* wsb = workspace + (int64_t)b * blocks * MN;
-      if (M <= 128) tn_skinny_kernel<1><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
+      if (M <= 128 && N <= 2) tn_skinny_kernel<1, 2><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
+      else if (M <= 128) tn_skinny_kernel<1><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
       else if (M <= 256) tn_skinny_kernel<2><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
       else tn_skinny_kernel<4><<<blocks, SK_WARPS * 32, smem, st>>>(Ab, lda, Bb, ldb, K, (int)M, (int)N, per, wsb);
       IDD_LAUNCH_CHECK();

@@ -98,12 +98,21 @@ __global__ void __launch_bounds__(TW * 32)
     if (v < nvec) {
       const float4 h = __ldg(Hin + k * nvec + v);
       const float hv[4] = {h.x, h.y, h.z, h.w};
+      if (R == 2) {
+        // the lane's 4 x R weights are contiguous in W_alpha [D][R]: two 128-bit shared loads instead of eight scalar
+        // ones with an 8-way bank conflict (lane stride 8 floats); same fma order per relation as the loop below
+        const float4 w01 = reinterpret_cast<const float4*>(s_wa)[v * 2];
+        const float4 w23 = reinterpret_cast<const float4*>(s_wa)[v * 2 + 1];
+        z[0] = fmaf(hv[3], w23.z, fmaf(hv[2], w23.x, fmaf(hv[1], w01.z, fmaf(hv[0], w01.x, z[0]))));
+        z[1] = fmaf(hv[3], w23.w, fmaf(hv[2], w23.y, fmaf(hv[1], w01.w, fmaf(hv[0], w01.y, z[1]))));
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float* w = s_wa + (v * 4 + q) * R;
+        for (int q = 0; q < 4; ++q) {
+          const float* w = s_wa + (v * 4 + q) * R;
 #pragma unroll
-        for (int i = 0; i < RMAX; ++i)
-          if (i < R) z[i] = fmaf(hv[q], w[i], z[i]);
+          for (int i = 0; i < RMAX; ++i)
+            if (i < R) z[i] = fmaf(hv[q], w[i], z[i]);
+        }
       }
     }
   }

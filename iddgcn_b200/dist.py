@@ -433,12 +433,15 @@ class GridSpMM:
         return out
 
     # -- end to end with host buffers -----------------------------------------------------------------------
-    def step_host(self, Xh, dSh, Sh, dXh, chunks: int = 4):
+    def step_host(self, Xh, dSh, Sh, dXh, chunks: int = 4, overlap: bool = True):
         """One step with pinned HOST blocks in and out: X_local/dS_local up, S_local/dX_local down.
 
         Three streams: uploads, compute, downloads.  X (the smaller input) goes up first so that the all-gather and
         the forward start early; S flows back in row chunks while dS is still on its way up; the backward's own block is
-        cut into node chunks so that dX starts flowing back before the kernel has finished."""
+        cut into node chunks so that dX starts flowing back before the kernel has finished.
+        overlap=False holds every download until both uploads have landed (the kernels still run as data arrives):
+        on hosts where several GPUs share one PCIe uplink, simultaneous traffic in both directions from two GPUs is
+        slower than the two directions one after the other (profiles/r02_host_step_timeline_c4_8gpu_2x4.jsonl)."""
         lib, chk = self.lib, self._lib.check
         main = torch.cuda.current_stream(self.dev)
         tl = getattr(self, "timeline", None)           # debug: list collecting (label, event) pairs of this step
@@ -475,6 +478,8 @@ class GridSpMM:
         chk(lib.iddgcn_copy_async(self.dS.data_ptr(), dSh.data_ptr(), self.dS.numel() * 4, s_in.cuda_stream))
         mark("dS up", s_in)
         ev_ds = s_in.record_event()
+        if not overlap:
+            s_out.wait_event(ev_ds)
         main.wait_event(ev_x)
         if p2p:
             self._wait(K_AG, e)
@@ -531,13 +536,24 @@ class GridSpMM:
         self.dS.copy_(dSh, non_blocking=True)
         torch.cuda.synchronize(self.dev)
         h2d = dSh.numel() * 4 / (time.perf_counter() - t0) / 1e9
-        for _ in range(2):
-            self.step_host(Xh, dSh, Sh, dXh)
-        torch.cuda.synchronize(self.dev)
+        # copy schedule: both are tried (1 warm-up + 2 timed steps each, max over ranks) and the faster one is timed
+        probe = {}
+        for ov in (True, False):
+            self.step_host(Xh, dSh, Sh, dXh, overlap=ov)
+            torch.cuda.synchronize(self.dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                self.step_host(Xh, dSh, Sh, dXh, overlap=ov)
+            torch.cuda.synchronize(self.dev)
+            t = torch.tensor([(time.perf_counter() - t0) / 2], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            probe[ov] = float(t[0])
+        overlap = probe[True] <= probe[False]
         dist.barrier()
         t0 = time.perf_counter()
         for _ in range(k):
-            self.step_host(Xh, dSh, Sh, dXh)
+            self.step_host(Xh, dSh, Sh, dXh, overlap=overlap)
         torch.cuda.synchronize(self.dev)
         dt = torch.tensor([(time.perf_counter() - t0) / k, h2d, -h2d], dtype=torch.float64, device=self.dev)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -549,6 +565,9 @@ class GridSpMM:
                "per_rank_pcie_GBps": {"up+down_in_step": (up + down) / step_s / 1e9,
                                       "h2d_alone_all_ranks_at_once_min": h2d_min,
                                       "h2d_alone_all_ranks_at_once_max": h2d_max},
+               "copy_schedule": ("uploads and downloads overlapped" if overlap else
+                                 "downloads held until the uploads have landed"),
+               "copy_schedule_probe_ms": {"overlapped": probe[True] * 1e3, "uploads_then_downloads": probe[False] * 1e3},
                "api": "GridSpMM.step_host: pinned host blocks in/out on every rank (3-stream pipeline)"}
         del Xh, dSh, Sh, dXh
         return res

@@ -44,8 +44,8 @@ def _worker(rank, world, port, N, R, D, grid, exchange, tri, X, dS, out_dir):
         Sh = torch.zeros(eng.S.shape).pin_memory()
         dXh = torch.zeros((eng.n_rows, Dc)).pin_memory()
         eng.S.zero_(); eng.dX.zero_()
-        for _ in range(2):
-            eng.step_host(Xh, dSh, Sh, dXh, chunks=3)
+        eng.step_host(Xh, dSh, Sh, dXh, chunks=3)
+        eng.step_host(Xh, dSh, Sh, dXh, chunks=3, overlap=False)       # downloads held until the uploads have landed
         torch.cuda.synchronize()
         eng.check_timeouts()
         np.save(os.path.join(out_dir, f"Sh_{rank}.npy"), Sh.numpy())

@@ -856,14 +856,15 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
     else IDD_STREAM2(MODE_, true);                              \
   } while (0)
   // IDDGCN_TUNE=<k>: launch-shape variants of the headline instantiation (D=128, unweighted, no hub rows) for A/B runs
-  if (LPR == 32 && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff) {
+  if ((LPR == 32 || LPR == 8) && mode == IDDGCN_VALS_ONES && a.heavy_t == 0x7fffffff && a.add.n == 0) {
     const char* tv = getenv("IDDGCN_TUNE");
     const int k = tv ? atoi(tv) : 0;
     if (k > 0) {
 #define IDD_TUNE(U_, TPB_, MINB_, NA_)                                                                              \
       do {                                                                                                          \
         const int64_t nb = (rows + (TPB_ / 32) * 32 - 1) / ((TPB_ / 32) * 32);                                      \
-        stream_rows_kernel<32, U_, IDDGCN_VALS_ONES, USE_PERM, false, TPB_, MINB_, NA_><<<(unsigned)nb, TPB_, 0, st>>>( \
+        stream_rows_kernel<(LPR == 8 ? 8 : 32), U_, IDDGCN_VALS_ONES, USE_PERM, false, TPB_, MINB_, NA_>            \
+            <<<(unsigned)nb, TPB_, 0, st>>>(                                                                        \
             a.ptr, a.idx, a.perm, a.vals, a.src, a.out, a.row_begin, a.row_end, a.nvec, a.add, a.heavy_t);   \
       } while (0)
       switch (k) {
@@ -879,6 +880,8 @@ static int launch_stream_mode(const StreamArgs& a, int mode, cudaStream_t st) {
         case 10: IDD_TUNE(8, 256, 1, false); break;
         case 11: IDD_TUNE(8, 256, 3, false); break;
         case 12: IDD_TUNE(10, 256, 3, false); break;
+        case 13: IDD_TUNE(4, 256, 8, false); break;
+        case 14: IDD_TUNE(2, 256, 8, false); break;
         default: IDD_TUNE(8, 256, 4, false); break;
       }
 #undef IDD_TUNE

@@ -50,3 +50,47 @@ def test_our_arm_line_on_small_workload():
     assert c["kind"] == "port" and c["cores"] >= 1 and 0 < c["value"] < d["value"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+
+
+def test_parity_check_detects_errors_and_passes_on_correct_data():
+    """bench.parity_check is the only correctness evidence the driver gets for N > 1 runs, so the checker itself is
+    tested on the CPU: fed the right S / dX blocks of a grid rank (row block 1 of 2, column group 1 of 2) it reports
+    0.0; a single wrong element, a missing edge contribution or a swapped row block is reported above the bar."""
+    import sys
+    from types import SimpleNamespace
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import cref
+    N, R, D, per_rel = 6000, 2, 16, 40000
+    raw = [bench.raw_edges(N, per_rel, r) for r in range(R)]
+    lo, hi, Dc, pc = 3000, 6000, 8, 1
+    n_rows = hi - lo
+    X = bench.gen_rows_np("X", np.arange(N), pc * Dc, Dc, D)
+    dS_full = bench.gen_rows_np("dS", np.arange(R * N), pc * Dc, Dc, D).reshape(R, N, Dc)
+    S = np.zeros((R, n_rows, Dc), np.float32)
+    dX = np.zeros((N, Dc), np.float32)
+    for r, (h, t) in enumerate(raw):
+        key = np.unique(h * N + t)
+        hh, tt = key // N, key % N
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(hh, minlength=N))]).astype(np.int32)
+        S[r] = cref.spmm_csr(ptr, tt.astype(np.int32), None, X)[lo:hi]            # rows of this rank's block
+        order = np.lexsort((hh, tt))                                               # by tail, then head
+        cptr = np.concatenate([[0], np.cumsum(np.bincount(tt, minlength=N))]).astype(np.int32)
+        dX += cref.spmm_csr(cptr, hh[order].astype(np.int32), None, dS_full[r])   # all row blocks contribute
+    eng = SimpleNamespace(dev=torch.device("cpu"), Dc=Dc, pc=pc, lo=lo, n_rows=n_rows,
+                          S=torch.from_numpy(S.copy()), dX=torch.from_numpy(dX[lo:hi].copy()))
+    ok = bench.parity_check(torch, eng, raw, N, R, D, n_rows, seed=1)
+    assert ok["rows"] == n_rows and ok["max_rel_err"] < 1e-6 and ok["edges"] > 70000
+    eng.S[1, 77, 3] += 0.01                                                        # one wrong element of S
+    assert bench.parity_check(torch, eng, raw, N, R, D, n_rows, seed=1)["fwd_rel_err"] > 1e-5
+    eng.S = torch.from_numpy(S.copy())
+    eng.dX = torch.from_numpy((dX[lo:hi] - dS_full[0, 10]).copy())                 # a contribution missing everywhere
+    assert bench.parity_check(torch, eng, raw, N, R, D, n_rows, seed=1)["bwd_rel_err"] > 1e-5
+    eng.dX = torch.from_numpy(dX[0:3000].copy())                                   # the other rank's block
+    assert bench.parity_check(torch, eng, raw, N, R, D, n_rows, seed=1)["bwd_rel_err"] > 1e-2
+    part = bench.parity_check(torch, SimpleNamespace(dev=torch.device("cpu"), Dc=Dc, pc=pc, lo=lo, n_rows=n_rows,
+                                                     S=torch.from_numpy(S.copy()), dX=torch.from_numpy(dX[lo:hi].copy())),
+                              raw, N, R, D, 500, seed=2)                            # a sample of 500 rows
+    assert part["rows"] == 500 and part["max_rel_err"] < 1e-6

@@ -467,7 +467,7 @@ class GridSpMM:
         if p2p:
             # the NVLink push goes on its own stream: s_in carries nothing but host->device copies and s_out nothing but
             # device->host copies (with the push queued between the two uploads the downloads were starved while dS
-            # was on its way up: profiles/r02_host_step_timeline_2gpu.json)
+            # was on its way up: profiles/r02_host_step_timeline_1gpu_2gpu.jsonl)
             self.epoch += 1
             e = self.epoch
             side = self.s_side

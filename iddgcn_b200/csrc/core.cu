@@ -113,7 +113,7 @@ extern "C" {
 
 const char* iddgcn_last_error(void) { return iddgcn::t_error; }
 
-const char* iddgcn_version(void) { return "iddgcn_b200 0.1.0 sm_100a"; }
+const char* iddgcn_version(void) { return "iddgcn_b200 0.2.0 sm_100a"; }
 
 int64_t iddgcn_launch_count(void) { return iddgcn::g_launches.load(std::memory_order_relaxed); }
 
